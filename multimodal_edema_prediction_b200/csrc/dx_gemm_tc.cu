@@ -1,0 +1,334 @@
+// bf16 GEMM on 5th-gen tensor cores: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
+// tcgen05.mma kind::f16 (one elected thread) -> fp32 accumulator in TMEM -> tcgen05.ld epilogue.
+//
+//   acc[m,n] = sum_k A(m,k) * B(n,k); A and B each K-major or MN-major (so X@W^T, dY@W and dY^T@X all run
+//   from the tensors as they sit in HBM, without transposed copies).
+//
+// CTA = 128 x BN output tile, BLOCK_K = 64 (one 128 B swizzle row of bf16), STAGES-deep mbarrier ring.
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// Large-K shapes use BN=256 / 4 stages (1 CTA per SM, 96 B/clk smem operand traffic per MMA);
+// small-K, HBM-bound shapes use BN=128 / 2-3 stages so that 2-3 CTAs share an SM and epilogues overlap mainloops.
+#include "dx_gemm_epilogue.cuh"
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int NTHREADS = 192;
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("dx_gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct TcParams {
+  int K;
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // descriptor byte offsets (test-overridable)
+};
+
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, TcParams p,
+                                                             DxEpi e) {
+  constexpr int A_BYTES = BM * BK * 2;
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024 B alignment is required by the 128B swizzle atoms; align manually as well.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
+        const int k0 = kb * BK;
+        if (!A_MN) {
+          tma_load_2d(sa, &tmA, full_bar + s, k0, m0);  // box {64 k, 128 m}
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, full_bar + s, m0 + c * 64, k0);  // {64 m, 64 k}
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &tmB, full_bar + s, k0, n0);  // box {64 k, BN n}
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, full_bar + s, n0 + c * 64, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+      // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle row.
+          // MN-major: advance 16 k-rows = two 1024 B swizzle atoms.
+          const uint64_t ad = make_smem_desc(sa + (A_MN ? k * 2048 : k * 32), p.a_lbo, p.a_sbo);
+          const uint64_t bd = make_smem_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
+          umma_f16(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue: warp w reads TMEM lanes [32*(w%4), +32) =====
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    float rs = 0.f, rd = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);  // warp-collective
+      if (m < e.M) dx_epilogue_chunk<32>(e, m, n0 + c * 32, v, rs, rd);
+    }
+    if (m < e.M) dx_epilogue_flush_row(e, m, rs, rd);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+int get_encode_fn() {
+  if (g_encode) return DX_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  DX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !fn) {
+    dx_set_error("cuTensorMapEncodeTiled not available from the driver");
+    return DX_ERR_CUDA;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return DX_OK;
+}
+
+// 2-D bf16 tensor map: dim0 = contiguous (size inner), dim1 = rows (size outer, stride ld elements).
+int make_tmap(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_inner,
+              int box_outer) {
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    dx_set_error("cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld ld=%lld box=%dx%d base=%p", (int)r, inner,
+                 outer, ld, box_inner, box_outer, base);
+    return DX_ERR_CUDA;
+  }
+  return DX_OK;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, const DxEpi& e,
+               cudaStream_t stream) {
+  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  auto kern = dx_gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done = true;
+  }
+  dim3 grid(dx_ceil_div(d->N, BN), dx_ceil_div(d->M, BM));
+  kern<<<grid, NTHREADS, SMEM, stream>>>(ta, tb, p, e);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_major(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& ta, const CUtensorMap& tb,
+                 const TcParams& p, const DxEpi& e, cudaStream_t stream) {
+  if (bn == 256 && stages == 4) return launch_cfg<256, 4, A_MN, B_MN>(d, ta, tb, p, e, stream);
+  if (bn == 128 && stages == 3) return launch_cfg<128, 3, A_MN, B_MN>(d, ta, tb, p, e, stream);
+  if (bn == 128 && stages == 6) return launch_cfg<128, 6, A_MN, B_MN>(d, ta, tb, p, e, stream);
+  if (bn == 64 && stages == 4) return launch_cfg<64, 4, A_MN, B_MN>(d, ta, tb, p, e, stream);
+  dx_set_error("dx_gemm_tc: unsupported tile config BN=%d stages=%d", bn, stages);
+  return DX_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int a_sbo, int b_lbo, int b_sbo,
+                      cudaStream_t stream) {
+  int rc = get_encode_fn();
+  if (rc) return rc;
+  DX_CHECK_ARG(d->in_dtype == DX_BF16, "dx_gemm_tc: inputs must be bf16");
+  DX_CHECK_ARG(((uintptr_t)d->A % 16 == 0) && ((uintptr_t)d->B % 16 == 0), "dx_gemm_tc: A/B must be 16 B aligned");
+  DX_CHECK_ARG((d->lda % 8 == 0) && (d->ldb % 8 == 0), "dx_gemm_tc: lda/ldb must be multiples of 8 (got %lld, %lld)",
+               (long long)d->lda, (long long)d->ldb);
+  if (bn <= 0) {
+    // Heuristic: deep-K contractions get the 128x256 tile; shallow-K (HBM-bound) ones get 128x128 with
+    // several CTAs per SM; narrow outputs get 128x64.
+    if (d->N <= 64) { bn = 64; stages = 4; }
+    else if (d->K >= 1024 && d->N >= 256) { bn = 256; stages = 4; }
+    else if (d->K >= 1024) { bn = 128; stages = 6; }
+    else { bn = 128; stages = 3; }
+  }
+  CUtensorMap ta, tb;
+  if (!d->a_mn) rc = make_tmap(&ta, d->A, d->K, d->M, d->lda, BK, BM);
+  else rc = make_tmap(&ta, d->A, d->M, d->K, d->lda, 64, BK);
+  if (rc) return rc;
+  if (!d->b_mn) rc = make_tmap(&tb, d->B, d->K, d->N, d->ldb, BK, bn);
+  else rc = make_tmap(&tb, d->B, d->N, d->K, d->ldb, 64, BK);
+  if (rc) return rc;
+  TcParams p;
+  p.K = d->K;
+  // K-major SW128: LBO unused (canonical value 1 -> 16 B), SBO = 8 rows * 128 B.
+  // MN-major SW128: LBO = distance between 64-element MN chunks (one 64x64 TMA box = 8192 B),
+  //                 SBO = distance between 8-row K groups (1024 B).
+  p.a_lbo = a_lbo >= 0 ? a_lbo : (d->a_mn ? 8192 : 16);
+  p.a_sbo = a_sbo >= 0 ? a_sbo : 1024;
+  p.b_lbo = b_lbo >= 0 ? b_lbo : (d->b_mn ? 8192 : 16);
+  p.b_sbo = b_sbo >= 0 ? b_sbo : 1024;
+  DxEpi e = dx_make_epi(d);
+  if (!d->a_mn && !d->b_mn) return launch_major<false, false>(d, bn, stages, ta, tb, p, e, stream);
+  if (!d->a_mn && d->b_mn) return launch_major<false, true>(d, bn, stages, ta, tb, p, e, stream);
+  if (d->a_mn && !d->b_mn) return launch_major<true, false>(d, bn, stages, ta, tb, p, e, stream);
+  return launch_major<true, true>(d, bn, stages, ta, tb, p, e, stream);
+}
