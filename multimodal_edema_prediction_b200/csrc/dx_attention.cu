@@ -1,0 +1,349 @@
+// Unmasked multi-head softmax attention for tiny sequences (DuETT: S = V+1 event tokens or T+1 time tokens,
+// head dim d/2; perceiver: 7 pathology queries over 1369 patch / 24 hour tokens).  x_transformers Attention core
+// (duett/duett.py:95-105) and nn.MultiheadAttention core (models/main_architecture_duett.py:752): softmax(q k^T / sqrt(dh)) v
+// with fp32 softmax.  The whole problem lives in shared memory/registers; FLOPs are <0.3 % of the step,
+// so this is a warp-shuffle FFMA kernel, not a tensor-core one.
+//
+// forward : one thread group (TPQ lanes) per query row, keys/values streamed through shared memory in tiles of 64,
+//           online softmax; writes o and the row log-sum-exp.
+// backward: kernel A (per query) -> D = <do,o>, dq ; kernel B (per key) -> dk, dv, streaming query tiles.
+#include "dx_common.cuh"
+#include "../../include/duett_b200.h"
+
+namespace {
+
+constexpr int KT = 64;    // keys (or queries) per shared-memory tile
+constexpr int NTH = 128;  // threads per block
+
+struct AttnView {      // element (b, s, head h, i) at base + b*bs + s*rs + h*dh + i
+  const void* p;
+  long long bs, rs;
+};
+struct AttnViewW {
+  void* p;
+  long long bs, rs;
+};
+
+template <typename T>
+__device__ __forceinline__ float ldv(const void* base, long long off) {
+  return dx_ld(reinterpret_cast<const T*>(base) + off);
+}
+
+// Loads `rows` rows x DH of a [S, DH]-strided head slice into shared memory as fp32 (zero padded).
+template <typename T, int DH>
+__device__ __forceinline__ void load_tile(float* sm, const AttnView& v, int b, int h, int s0, int S) {
+  for (int idx = threadIdx.x; idx < KT * DH; idx += NTH) {
+    const int r = idx / DH, i = idx - r * DH;
+    const int s = s0 + r;
+    sm[idx] = (s < S) ? ldv<T>(v.p, (long long)b * v.bs + (long long)s * v.rs + h * DH + i) : 0.f;
+  }
+}
+
+template <typename T, int DH, int TPQ>
+__global__ void __launch_bounds__(NTH) attn_fwd_kernel(AttnView q, AttnView k, AttnView v, AttnViewW o, float* lse,
+                                                      int H, int Sq, int Sk, float scale) {
+  constexpr int DHT = DH / TPQ;
+  extern __shared__ float smem[];
+  float* sk = smem;
+  float* sv = smem + KT * DH;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int qi = blockIdx.y * (NTH / TPQ) + threadIdx.x / TPQ;
+  const int part = threadIdx.x % TPQ;
+  const bool active = qi < Sq;
+  float qr[DHT], acc[DHT];
+#pragma unroll
+  for (int i = 0; i < DHT; ++i) {
+    qr[i] = active ? ldv<T>(q.p, (long long)b * q.bs + (long long)qi * q.rs + h * DH + part * DHT + i) * scale : 0.f;
+    acc[i] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < Sk; k0 += KT) {
+    __syncthreads();
+    load_tile<T, DH>(sk, k, b, h, k0, Sk);
+    load_tile<T, DH>(sv, v, b, h, k0, Sk);
+    __syncthreads();
+    const int kn = min(KT, Sk - k0);
+    for (int j = 0; j < kn; ++j) {
+      const float* kj = sk + j * DH + part * DHT;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < DHT; ++i) s = fmaf(qr[i], kj[i], s);
+#pragma unroll
+      for (int off = 1; off < TPQ; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (s > m) {
+        const float corr = __expf(m - s);
+        l *= corr;
+#pragma unroll
+        for (int i = 0; i < DHT; ++i) acc[i] *= corr;
+        m = s;
+      }
+      const float p = __expf(s - m);
+      l += p;
+      const float* vj = sv + j * DH + part * DHT;
+#pragma unroll
+      for (int i = 0; i < DHT; ++i) acc[i] = fmaf(p, vj[i], acc[i]);
+    }
+  }
+  if (active) {
+    const float inv = 1.f / l;
+    T* op = reinterpret_cast<T*>(o.p) + (long long)b * o.bs + (long long)qi * o.rs + h * DH + part * DHT;
+#pragma unroll
+    for (int i = 0; i < DHT; ++i) dx_st(op + i, acc[i] * inv);
+    if (part == 0 && lse) lse[((long long)b * H + h) * Sq + qi] = m + __logf(l);
+  }
+}
+
+// Kernel A: per query -> D_i = <do_i, o_i>, dq_i = scale * sum_j p_ij (do_i.v_j - D_i) k_j
+template <typename T, int DH, int TPQ>
+__global__ void __launch_bounds__(NTH) attn_bwd_q_kernel(AttnView q, AttnView k, AttnView v, AttnView o, AttnView go,
+                                                        AttnViewW dq, const float* lse, float* Dv, int H, int Sq, int Sk,
+                                                        float scale) {
+  constexpr int DHT = DH / TPQ;
+  extern __shared__ float smem[];
+  float* sk = smem;
+  float* sv = smem + KT * DH;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int qi = blockIdx.y * (NTH / TPQ) + threadIdx.x / TPQ;
+  const int part = threadIdx.x % TPQ;
+  const bool active = qi < Sq;
+  float qr[DHT], gr[DHT], acc[DHT];
+  float D = 0.f;
+#pragma unroll
+  for (int i = 0; i < DHT; ++i) {
+    const long long hoff = h * DH + part * DHT + i;
+    qr[i] = active ? ldv<T>(q.p, (long long)b * q.bs + (long long)qi * q.rs + hoff) * scale : 0.f;
+    gr[i] = active ? ldv<T>(go.p, (long long)b * go.bs + (long long)qi * go.rs + hoff) : 0.f;
+    const float ov = active ? ldv<T>(o.p, (long long)b * o.bs + (long long)qi * o.rs + hoff) : 0.f;
+    D = fmaf(gr[i], ov, D);
+    acc[i] = 0.f;
+  }
+#pragma unroll
+  for (int off = 1; off < TPQ; off <<= 1) D += __shfl_xor_sync(0xffffffffu, D, off);
+  const float L = active ? lse[((long long)b * H + h) * Sq + qi] : 0.f;
+  for (int k0 = 0; k0 < Sk; k0 += KT) {
+    __syncthreads();
+    load_tile<T, DH>(sk, k, b, h, k0, Sk);
+    load_tile<T, DH>(sv, v, b, h, k0, Sk);
+    __syncthreads();
+    const int kn = min(KT, Sk - k0);
+    for (int j = 0; j < kn; ++j) {
+      const float* kj = sk + j * DH + part * DHT;
+      const float* vj = sv + j * DH + part * DHT;
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < DHT; ++i) {
+        s = fmaf(qr[i], kj[i], s);
+        dp = fmaf(gr[i], vj[i], dp);
+      }
+#pragma unroll
+      for (int off = 1; off < TPQ; off <<= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        dp += __shfl_xor_sync(0xffffffffu, dp, off);
+      }
+      const float ds = __expf(s - L) * (dp - D);
+#pragma unroll
+      for (int i = 0; i < DHT; ++i) acc[i] = fmaf(ds, kj[i], acc[i]);
+    }
+  }
+  if (active) {
+    T* dp_ = reinterpret_cast<T*>(dq.p) + (long long)b * dq.bs + (long long)qi * dq.rs + h * DH + part * DHT;
+#pragma unroll
+    for (int i = 0; i < DHT; ++i) dx_st(dp_ + i, acc[i] * scale);
+    if (part == 0) Dv[((long long)b * H + h) * Sq + qi] = D;
+  }
+}
+
+// Kernel B: per key -> dv_j = sum_i p_ij do_i ; dk_j = scale * sum_i p_ij (do_i.v_j - D_i) q_i
+template <typename T, int DH, int TPQ>
+__global__ void __launch_bounds__(NTH) attn_bwd_kv_kernel(AttnView q, AttnView k, AttnView v, AttnView go, AttnViewW dk,
+                                                         AttnViewW dv, const float* lse, const float* Dv, int H, int Sq,
+                                                         int Sk, float scale) {
+  constexpr int DHT = DH / TPQ;
+  extern __shared__ float smem[];
+  float* sq = smem;
+  float* sg = smem + KT * DH;
+  float* sl = smem + 2 * KT * DH;  // lse tile
+  float* sd = sl + KT;             // D tile
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int kj = blockIdx.y * (NTH / TPQ) + threadIdx.x / TPQ;
+  const int part = threadIdx.x % TPQ;
+  const bool active = kj < Sk;
+  float kr[DHT], vr[DHT], ak[DHT], av[DHT];
+#pragma unroll
+  for (int i = 0; i < DHT; ++i) {
+    const long long hoff = h * DH + part * DHT + i;
+    kr[i] = active ? ldv<T>(k.p, (long long)b * k.bs + (long long)kj * k.rs + hoff) : 0.f;
+    vr[i] = active ? ldv<T>(v.p, (long long)b * v.bs + (long long)kj * v.rs + hoff) : 0.f;
+    ak[i] = 0.f;
+    av[i] = 0.f;
+  }
+  for (int q0 = 0; q0 < Sq; q0 += KT) {
+    __syncthreads();
+    load_tile<T, DH>(sq, q, b, h, q0, Sq);
+    load_tile<T, DH>(sg, go, b, h, q0, Sq);
+    if (threadIdx.x < KT) {
+      const int s = q0 + threadIdx.x;
+      sl[threadIdx.x] = s < Sq ? lse[((long long)b * H + h) * Sq + s] : 0.f;
+      sd[threadIdx.x] = s < Sq ? Dv[((long long)b * H + h) * Sq + s] : 0.f;
+    }
+    __syncthreads();
+    const int qn = min(KT, Sq - q0);
+    for (int i2 = 0; i2 < qn; ++i2) {
+      const float* qi = sq + i2 * DH + part * DHT;
+      const float* gi = sg + i2 * DH + part * DHT;
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < DHT; ++i) {
+        s = fmaf(qi[i], kr[i], s);
+        dp = fmaf(gi[i], vr[i], dp);
+      }
+#pragma unroll
+      for (int off = 1; off < TPQ; off <<= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        dp += __shfl_xor_sync(0xffffffffu, dp, off);
+      }
+      const float p = __expf(s * scale - sl[i2]);
+      const float ds = p * (dp - sd[i2]);
+#pragma unroll
+      for (int i = 0; i < DHT; ++i) {
+        av[i] = fmaf(p, gi[i], av[i]);
+        ak[i] = fmaf(ds, qi[i], ak[i]);
+      }
+    }
+  }
+  if (active) {
+    T* dkp = reinterpret_cast<T*>(dk.p) + (long long)b * dk.bs + (long long)kj * dk.rs + h * DH + part * DHT;
+    T* dvp = reinterpret_cast<T*>(dv.p) + (long long)b * dv.bs + (long long)kj * dv.rs + h * DH + part * DHT;
+#pragma unroll
+    for (int i = 0; i < DHT; ++i) {
+      dx_st(dkp + i, ak[i] * scale);
+      dx_st(dvp + i, av[i]);
+    }
+  }
+}
+
+// rowdot[n] = <a[n,:], g[n,:]>;  g[n,:] *= row_scale[n]   (ScaleNorm-backward bookkeeping on the small [N,3d] tensors)
+template <typename T>
+__global__ void __launch_bounds__(256) rowdot_scale_kernel(const T* __restrict__ a, T* __restrict__ g,
+                                                          const float* __restrict__ row_scale, float* __restrict__ rowdot,
+                                                          int N, int C) {
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const T* ar = a + (long long)warp * C;
+  T* gr = g + (long long)warp * C;
+  const float s = row_scale ? row_scale[warp] : 1.f;
+  float dot = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float gv = dx_ld(gr + c);
+    dot = fmaf(dx_ld(ar + c), gv, dot);
+    if (row_scale) dx_st(gr + c, gv * s);
+  }
+  dot = dx_warp_sum(dot);
+  if (lane == 0 && rowdot) rowdot[warp] = dot;
+}
+
+// row_scale[n] = c * g / max(sqrt(rowsq[n]), eps)
+__global__ void scalenorm_scale_kernel(const float* __restrict__ rowsq, const float* __restrict__ g, float c,
+                                       float* __restrict__ out, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] = c * g[0] / fmaxf(sqrtf(rowsq[i]), 1e-12f);
+}
+
+template <typename T, int DH, int TPQ>
+int launch_fwd(const AttnView& q, const AttnView& k, const AttnView& v, const AttnViewW& o, float* lse, int B, int H,
+               int Sq, int Sk, float scale, cudaStream_t st) {
+  const size_t smem = 2 * KT * DH * sizeof(float);
+  auto kern = attn_fwd_kernel<T, DH, TPQ>;
+  if (smem > 48 * 1024) DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(B * H, dx_ceil_div(Sq, NTH / TPQ));
+  kern<<<grid, NTH, smem, st>>>(q, k, v, o, lse, H, Sq, Sk, scale);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
+template <typename T, int DH, int TPQ>
+int launch_bwd(const AttnView& q, const AttnView& k, const AttnView& v, const AttnView& o, const AttnView& go,
+               const AttnViewW& dq, const AttnViewW& dk, const AttnViewW& dv, const float* lse, float* Dv, int B, int H,
+               int Sq, int Sk, float scale, cudaStream_t st) {
+  const size_t smem_q = 2 * KT * DH * sizeof(float);
+  const size_t smem_kv = (2 * KT * DH + 2 * KT) * sizeof(float);
+  auto kq = attn_bwd_q_kernel<T, DH, TPQ>;
+  auto kkv = attn_bwd_kv_kernel<T, DH, TPQ>;
+  if (smem_kv > 48 * 1024) {
+    DX_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+    DX_CUDA(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+  }
+  dim3 gq(B * H, dx_ceil_div(Sq, NTH / TPQ));
+  kq<<<gq, NTH, smem_q, st>>>(q, k, v, o, go, dq, lse, Dv, H, Sq, Sk, scale);
+  DX_LAUNCH_CHECK();
+  dim3 gk(B * H, dx_ceil_div(Sk, NTH / TPQ));
+  kkv<<<gk, NTH, smem_kv, st>>>(q, k, v, go, dk, dv, lse, Dv, H, Sq, Sk, scale);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
+#define DX_ATTN_DISPATCH(T, CALL)                                                     \
+  switch (dh) {                                                                       \
+    case 4: return CALL(T, 4, 1);                                                     \
+    case 8: return CALL(T, 8, 1);                                                     \
+    case 12: return CALL(T, 12, 1);                                                   \
+    case 16: return CALL(T, 16, 1);                                                   \
+    case 32: return CALL(T, 32, 1);                                                   \
+    case 64: return CALL(T, 64, 2);                                                   \
+    case 128: return CALL(T, 128, 4);                                                 \
+    default:                                                                          \
+      dx_set_error("dx_attn: unsupported head dim %d (supported 4,8,12,16,32,64,128)", dh); \
+      return DX_ERR_UNSUPPORTED;                                                      \
+  }
+
+}  // namespace
+
+extern "C" {
+
+/* q/k/v/o: element (b,s,h,i) at ptr + b*bs + s*rs + h*dh + i (strides in elements). */
+int dx_attn_fwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_rs, const void* v,
+                int64_t v_bs, int64_t v_rs, void* o, int64_t o_bs, int64_t o_rs, float* lse, int B, int H, int Sq, int Sk,
+                int dh, int dtype, void* stream) {
+  DX_CHECK_ARG(q && k && v && o, "dx_attn_fwd: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  AttnView Q{q, q_bs, q_rs}, K{k, k_bs, k_rs}, V{v, v_bs, v_rs};
+  AttnViewW O{o, o_bs, o_rs};
+  const float scale = 1.f / sqrtf((float)dh);
+#define CALL_FWD(T, DH, TPQ) launch_fwd<T, DH, TPQ>(Q, K, V, O, lse, B, H, Sq, Sk, scale, st)
+  if (dtype == DX_BF16) { DX_ATTN_DISPATCH(bf16, CALL_FWD) } else { DX_ATTN_DISPATCH(float, CALL_FWD) }
+#undef CALL_FWD
+}
+
+int dx_attn_bwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_rs, const void* v,
+                int64_t v_bs, int64_t v_rs, const void* o, int64_t o_bs, int64_t o_rs, const void* go, int64_t go_bs,
+                int64_t go_rs, void* dq, int64_t dq_bs, int64_t dq_rs, void* dk, int64_t dk_bs, int64_t dk_rs, void* dv,
+                int64_t dv_bs, int64_t dv_rs, const float* lse, float* D_ws, int B, int H, int Sq, int Sk, int dh,
+                int dtype, void* stream) {
+  DX_CHECK_ARG(q && k && v && o && go && dq && dk && dv && lse && D_ws, "dx_attn_bwd: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  AttnView Q{q, q_bs, q_rs}, K{k, k_bs, k_rs}, V{v, v_bs, v_rs}, O{o, o_bs, o_rs}, GO{go, go_bs, go_rs};
+  AttnViewW DQ{dq, dq_bs, dq_rs}, DK{dk, dk_bs, dk_rs}, DV{dv, dv_bs, dv_rs};
+  const float scale = 1.f / sqrtf((float)dh);
+#define CALL_BWD(T, DH, TPQ) launch_bwd<T, DH, TPQ>(Q, K, V, O, GO, DQ, DK, DV, lse, D_ws, B, H, Sq, Sk, scale, st)
+  if (dtype == DX_BF16) { DX_ATTN_DISPATCH(bf16, CALL_BWD) } else { DX_ATTN_DISPATCH(float, CALL_BWD) }
+#undef CALL_BWD
+}
+
+int dx_rowdot_scale(const void* a, void* g, const float* row_scale, float* rowdot, int N, int C, int dtype, void* stream) {
+  DX_CHECK_ARG(a && g, "dx_rowdot_scale: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = dx_ceil_div((long long)N * 32, 256);
+  if (dtype == DX_BF16) rowdot_scale_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)a, (bf16*)g, row_scale, rowdot, N, C);
+  else rowdot_scale_kernel<float><<<grid, 256, 0, st>>>((const float*)a, (float*)g, row_scale, rowdot, N, C);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
+int dx_scalenorm_scale(const float* rowsq, const float* g, float c, float* out, int N, void* stream) {
+  DX_CHECK_ARG(rowsq && g && out, "dx_scalenorm_scale: null tensor");
+  scalenorm_scale_kernel<<<dx_ceil_div(N, 256), 256, 0, (cudaStream_t)stream>>>(rowsq, g, c, out, N);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,354 @@
+"""Thin Python wrappers over the C ABI (include/duett_b200.h).  Every function launches hand-written sm_100a
+kernels on the current CUDA stream; tensors are only used for their device memory.  No CPU fallback exists: a
+missing library or a non-zero status raises."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, ACT_RELU_BWD, ACT_TANH, ACT_TANH_BWD, gemm  # noqa: F401
+
+_launches = 0   # kernels-launching C calls issued (bench.py reports it as gpu_launches)
+
+
+def launches() -> int:
+    return _launches
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _call(name, *args):
+    global _launches
+    _launches += 1
+    L.check(getattr(L.lib(), name)(*args, torch.cuda.current_stream().cuda_stream))
+
+
+def _dt(t: torch.Tensor) -> int:
+    return L.dtype_code(t.dtype)
+
+
+def _chk(t, dtype=None, contiguous=True):
+    assert t.is_cuda, "duett_b200 ops need CUDA tensors (there is no CPU path)"
+    if contiguous:
+        assert t.is_contiguous(), "tensor must be contiguous"
+    if dtype is not None:
+        assert t.dtype == dtype, (t.dtype, dtype)
+    return t
+
+
+def gemm_(a, b, **kw):
+    global _launches
+    _launches += 1
+    gemm(a, b, **kw)
+
+
+# ---- relayout / norms -------------------------------------------------------------------------------------------------
+def relayout_fwd(src, B, P, Q, d, *, src_rowsq=None, g=None, pos_bcast=None, pos_batched=None, want_rowsq=True):
+    """dst[b,q,p,:] = src[b,p,q,:] * final_norm_scale[b,p] + pos ; returns (dst [B,Q,P,d], rowsq [B*Q] or None)."""
+    _chk(src)
+    dst = torch.empty((B, Q, P, d), device=src.device, dtype=src.dtype)
+    rowsq = torch.empty(B * Q, device=src.device, dtype=torch.float32) if want_rowsq else None
+    if pos_batched is not None:
+        assert pos_batched.dtype == src.dtype and pos_batched.is_contiguous()
+    _call("dx_relayout_fwd", _p(src), _p(src_rowsq), _p(g), _p(pos_bcast), _p(pos_batched), _p(dst), _p(rowsq), B, P, Q, d,
+          _dt(src))
+    return dst, rowsq
+
+
+def relayout_bwd(gdst, B, P, Q, d, *, src=None, src_rowsq=None, g=None, dg=None):
+    """grad wrt src [B,P,Q,d] given grad wrt dst [B,Q,P,d]; applies the final-ScaleNorm backward when src_rowsq is given."""
+    _chk(gdst)
+    dsrc = torch.empty((B, P, Q, d), device=gdst.device, dtype=gdst.dtype)
+    _call("dx_relayout_bwd", _p(gdst), _p(src), _p(src_rowsq), _p(g), _p(dsrc), _p(dg), B, P, Q, d, _dt(gdst))
+    return dsrc
+
+
+def colsum(x2d, out, accumulate=True):
+    """out[n] (+)= sum_m x2d[m, n]; x2d may be a row-strided 2-D view."""
+    assert x2d.dim() == 2 and x2d.stride(1) == 1
+    _chk(out, torch.float32)
+    _call("dx_colsum", _p(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], _p(out), int(accumulate), _dt(x2d))
+
+
+def axpy(x, y, alpha=1.0, accumulate=True):
+    _chk(x); _chk(y)
+    assert x.numel() == y.numel() and x.dtype == y.dtype
+    _call("dx_axpy", _p(x), _p(y), x.numel(), float(alpha), int(accumulate), _dt(x))
+
+
+def axpy_f32(x, y, alpha):
+    """y += alpha * x for small f32 vectors of any length (dx_axpy needs n % 8 == 0, so go through dx_scale/dx_colsum)."""
+    _chk(x, torch.float32); _chk(y, torch.float32)
+    n = x.numel()
+    if n % 8 == 0:
+        return axpy(x, y, alpha, accumulate=True)
+    xs = x.reshape(1, n) if alpha == 1.0 else (x * alpha).reshape(1, n)
+    colsum(xs, y, accumulate=True)
+
+
+def cast(x, dtype):
+    _chk(x)
+    if x.dtype == dtype:
+        return x
+    y = torch.empty(x.shape, device=x.device, dtype=dtype)
+    _call("dx_cast", _p(x), _dt(x), _p(y), _dt(y), x.numel())
+    return y
+
+
+def scalenorm_scale(rowsq, g, dim):
+    out = torch.empty_like(rowsq)
+    _call("dx_scalenorm_scale", _p(rowsq), _p(g), float(dim) ** 0.5, _p(out), rowsq.numel())
+    return out
+
+
+def rowdot_scale(a, g, row_scale):
+    """returns rowdot[n] = <a[n], g[n]>; scales g[n] by row_scale[n] in place."""
+    _chk(a); _chk(g)
+    N, Cc = a.shape
+    rd = torch.empty(N, device=a.device, dtype=torch.float32)
+    _call("dx_rowdot_scale", _p(a), _p(g), _p(row_scale), _p(rd), N, Cc, _dt(a))
+    return rd
+
+
+# ---- attention ---------------------------------------------------------------------------------------------------------
+def _view3(t):
+    """(ptr tensor, batch stride, row stride) of a [B,S,*] tensor whose last dim is dense."""
+    assert t.dim() == 3 and t.stride(2) == 1
+    return t, t.stride(0), t.stride(1)
+
+
+def attn_fwd(q, k, v, heads):
+    """q [B,Sq,h*dh], k/v [B,Sk,h*dh] (strided views allowed) -> o [B,Sq,h*dh], lse [B,h,Sq]."""
+    B, Sq, D = q.shape
+    Sk = k.shape[1]
+    dh = D // heads
+    o = torch.empty((B, Sq, D), device=q.device, dtype=q.dtype)
+    lse = torch.empty((B, heads, Sq), device=q.device, dtype=torch.float32)
+    args = []
+    for t in (q, k, v, o):
+        t_, bs, rs = _view3(t)
+        args += [_p(t_), bs, rs]
+    _call("dx_attn_fwd", *args, _p(lse), B, heads, Sq, Sk, dh, _dt(q))
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, go, lse, heads, dq, dk, dv):
+    B, Sq, D = q.shape
+    Sk = k.shape[1]
+    dh = D // heads
+    Dws = torch.empty((B, heads, Sq), device=q.device, dtype=torch.float32)
+    args = []
+    for t in (q, k, v, o, go, dq, dk, dv):
+        t_, bs, rs = _view3(t)
+        args += [_p(t_), bs, rs]
+    _call("dx_attn_bwd", *args, _p(lse), _p(Dws), B, heads, Sq, Sk, dh, _dt(q))
+
+
+# ---- embedding ---------------------------------------------------------------------------------------------------------
+def embed_fwd(xs, V, d, W0, b0, gamma, beta, run_mean, run_var, W4, b4, nobs, special, tab, act_dtype, training):
+    B, T, _ = xs.shape
+    dev = xs.device
+    psi = torch.empty((B, T + 1, V + 1, d), device=dev, dtype=act_dtype)
+    stats = torch.empty((V, 64, 2), device=dev, dtype=torch.float64) if training else None
+    mean = torch.empty((V, 64), device=dev, dtype=torch.float32)
+    rstd = torch.empty((V, 64), device=dev, dtype=torch.float32)
+    for t in (xs, W0, b0, gamma, beta, W4, b4, nobs, special, tab):
+        _chk(t, torch.float32)
+    _call("dx_embed_fwd", _p(xs), B, T, V, d, _p(W0), _p(b0), _p(gamma), _p(beta), _p(run_mean), _p(run_var), _p(W4), _p(b4),
+          _p(nobs), _p(special), _p(tab), _p(psi), L.dtype_code(act_dtype), _p(stats), _p(mean), _p(rstd), int(training))
+    return psi, mean, rstd
+
+
+def embed_bwd(xs, V, d, W0, b0, gamma, beta, W4, nobs, mean, rstd, dpsi, grads, training):
+    """grads: dict with f32 tensors dW0, db0, dgamma, dbeta, dW4, db4, dnobs, dspecial (accumulated). Returns dtab [B,d]."""
+    B, T, _ = xs.shape
+    dev = xs.device
+    dhn = torch.empty((V, B * T, 64), device=dev, dtype=torch.float32)
+    dgb = torch.empty((2, V, 64), device=dev, dtype=torch.float32)
+    dtab = torch.empty((B, d), device=dev, dtype=torch.float32)
+    _chk(dpsi)
+    _call("dx_embed_bwd", _p(xs), B, T, V, d, _p(W0), _p(b0), _p(gamma), _p(beta), _p(W4), _p(nobs), _p(mean), _p(rstd),
+          _p(dpsi), _dt(dpsi), _p(dhn), _p(dgb), _p(grads["dW0"]), _p(grads["db0"]), _p(grads["dgamma"]), _p(grads["dbeta"]),
+          _p(grads["dW4"]), _p(grads["db4"]), _p(grads["dnobs"]), _p(grads["dspecial"]), _p(dtab), int(training))
+    return dtab
+
+
+# ---- norms -------------------------------------------------------------------------------------------------------------
+def bn2d_fwd(x, w, b, run_mean, run_var, training):
+    _chk(x, torch.float32)
+    R, Cc = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    _call("dx_bn2d_fwd", _p(x), R, Cc, _p(w), _p(b), _p(run_mean), _p(run_var), _p(y), _p(mean), _p(rstd), int(training))
+    return y, mean, rstd
+
+
+def bn2d_bwd(dy, x, w, mean, rstd, dw, db, training, need_dx=True):
+    _chk(dy, torch.float32)
+    R, Cc = x.shape
+    dx = torch.empty_like(x) if need_dx else None
+    _call("dx_bn2d_bwd", _p(dy), _p(x), R, Cc, _p(w), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), int(training))
+    return dx
+
+
+def layernorm_fwd(x2d, w, b):
+    _chk(x2d)
+    R, Cc = x2d.shape
+    y = torch.empty_like(x2d)
+    mean = torch.empty(R, device=x2d.device, dtype=torch.float32)
+    rstd = torch.empty(R, device=x2d.device, dtype=torch.float32)
+    _call("dx_layernorm_fwd", _p(x2d), R, Cc, _p(w), _p(b), _p(y), _p(mean), _p(rstd), _dt(x2d))
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x2d, w, mean, rstd, dw, db, need_dx=True):
+    _chk(dy); _chk(x2d)
+    R, Cc = x2d.shape
+    dx = torch.empty_like(x2d) if need_dx else None
+    _call("dx_layernorm_bwd", _p(dy), _p(x2d), R, Cc, _p(w), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), _dt(x2d))
+    return dx
+
+
+# ---- pooling / gathers ---------------------------------------------------------------------------------------------------
+def mean_rows(x3d, T):
+    _chk(x3d)
+    B, T1, E = x3d.shape
+    y = torch.empty((B, E), device=x3d.device, dtype=torch.float32)
+    _call("dx_mean_rows", _p(x3d), _p(y), B, T1, T, E, _dt(x3d))
+    return y
+
+
+def mean_rows_bwd(dy, T1, T, dtype):
+    _chk(dy, torch.float32)
+    B, E = dy.shape
+    dx = torch.empty((B, T1, E), device=dy.device, dtype=dtype)
+    _call("dx_mean_rows_bwd", _p(dy), _p(dx), B, T1, T, E, L.dtype_code(dtype))
+    return dx
+
+
+def gather_vec(src, offsets, Lv):
+    _chk(src); _chk(offsets, torch.int64)
+    n = offsets.numel()
+    out = torch.empty((n, Lv), device=src.device, dtype=torch.float32)
+    _call("dx_gather_vec", _p(src), _p(offsets), _p(out), n, Lv, _dt(src))
+    return out
+
+
+def scatter_vec(src, offsets, dst, accumulate=True):
+    _chk(src, torch.float32); _chk(offsets, torch.int64); _chk(dst)
+    n, Lv = src.shape
+    _call("dx_scatter_vec", _p(src), _p(offsets), _p(dst), n, Lv, int(accumulate), _dt(dst))
+
+
+# ---- losses --------------------------------------------------------------------------------------------------------------
+def kd_loss(zs, zt, y, T, alpha, pos_weight, need_grad=True):
+    for t in (zs, zt, y):
+        _chk(t, torch.float32)
+    out = torch.empty(3, device=zs.device, dtype=torch.float32)
+    dz = torch.empty_like(zs) if need_grad else None
+    _call("dx_kd_loss", _p(zs), _p(zt), _p(y), zs.numel(), float(T), float(alpha),
+          -1.0 if pos_weight is None else float(pos_weight), 1e-7, _p(out), _p(dz))
+    return out, dz
+
+
+def bce_logits(z, y, w_pos=1.0, w_neg=1.0, need_grad=True):
+    _chk(z, torch.float32); _chk(y, torch.float32)
+    out = torch.empty(1, device=z.device, dtype=torch.float32)
+    dz = torch.empty_like(z) if need_grad else None
+    _call("dx_bce_logits", _p(z), _p(y), z.numel(), float(w_pos), float(w_neg), _p(out), _p(dz))
+    return out, dz
+
+
+def masked_mse_bce(yhat, phat, y, m, w_presence, out2, need_grad=True):
+    for t in (yhat, phat, y, m):
+        _chk(t, torch.float32)
+    d1 = torch.empty_like(yhat) if need_grad else None
+    d2 = torch.empty_like(phat) if need_grad else None
+    _call("dx_masked_mse_bce", _p(yhat), _p(phat), _p(y), _p(m), yhat.numel(), float(w_presence), _p(out2), _p(d1), _p(d2))
+    return d1, d2
+
+
+def masked_bce_cols(z, y, m, pos_weight, coef, eps, need_grad=True):
+    for t in (z, y, m):
+        _chk(t, torch.float32)
+    B, K = z.shape
+    per = torch.empty(K, device=z.device, dtype=torch.float32)
+    dz = torch.empty_like(z) if need_grad else None
+    _call("dx_masked_bce_cols", _p(z), _p(y), _p(m), _p(pos_weight), _p(coef), B, K, float(eps), _p(per), _p(dz))
+    return per, dz
+
+
+def aux_residual_kl(img_logits, scaled_corr, y, mask, eps=0.05, need_grad=True):
+    for t in (img_logits, scaled_corr, y, mask):
+        _chk(t, torch.float32)
+    out = torch.empty(1, device=y.device, dtype=torch.float32)
+    dc = torch.empty_like(scaled_corr) if need_grad else None
+    _call("dx_aux_residual_kl", _p(img_logits), _p(scaled_corr), _p(y), _p(mask), y.numel(), float(eps), _p(out), _p(dc))
+    return out, dc
+
+
+def require_device(t):
+    if not t.is_cuda:
+        raise L.DxError("duett_b200 has no CPU path: inputs must be CUDA tensors on a B200")
+
+
+def act_bwd(g, aux, act_bwd_code):
+    """g * act'(aux) (RELU_BWD / TANH_BWD: aux = activation output; GELU_BWD: aux = pre-activation)."""
+    _chk(g); _chk(aux)
+    out = torch.empty_like(g)
+    _call("dx_act_bwd", _p(g), _p(aux), _p(out), g.numel(), act_bwd_code, _dt(g))
+    return out
+
+
+def scale_dev(x, s):
+    """x * s with s a device tensor: 1 element (upstream loss gradient, no host sync) or [K] (per-column scale)."""
+    _chk(x, torch.float32)
+    out = torch.empty_like(x)
+    s = s.reshape(-1).float().contiguous()
+    _call("dx_scale_dev", _p(x), _p(s), _p(out), x.numel(), s.numel())
+    return out
+
+
+def sum_div_acc(x, g, sink):
+    """sink[0] += sum(x) / g[0]."""
+    _call("dx_sum_div_acc", _p(x), x.numel(), _p(g), _p(sink))
+
+
+def fusion_logits(hi, ht, corr, bias_i, bias_t, beta):
+    B, K = hi.shape
+    img, ts, scaled, fusion = (torch.empty_like(hi) for _ in range(4))
+    _call("dx_fusion_logits", _p(hi), _p(ht), _p(corr), _p(bias_i), _p(bias_t), _p(beta), _p(img), _p(ts), _p(scaled),
+          _p(fusion), B, K)
+    return img, ts, scaled, fusion
+
+
+def fusion_logits_bwd(d_img, d_ts, d_scaled, d_fus, corr, beta, dbeta, dbias_i, dbias_t):
+    B, K = corr.shape
+    d_corr = torch.empty_like(corr)
+    c = lambda t: None if t is None else t.contiguous()
+    d_img, d_ts, d_scaled, d_fus = c(d_img), c(d_ts), c(d_scaled), c(d_fus)
+    _call("dx_fusion_logits_bwd", _p(d_img), _p(d_ts), _p(d_scaled), _p(d_fus), _p(corr), _p(beta), _p(d_corr), _p(dbeta),
+          _p(dbias_i), _p(dbias_t), B, K)
+    return d_corr
+
+
+# ---- optimizer -------------------------------------------------------------------------------------------------------------
+def adamw(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale_dev=None, grad_scale=1.0):
+    for t in (p, g, m, v):
+        _chk(t, torch.float32)
+    _call("dx_adamw", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
+          float(weight_decay), int(step), _p(grad_scale_dev), float(grad_scale))
+
+
+def sumsq(x, out):
+    _chk(x, torch.float32)
+    _call("dx_sumsq", _p(x), x.numel(), _p(out))
+
+
+def clip_factor(sumsq_t, max_norm, clip):
+    _call("dx_clip_factor", _p(sumsq_t), float(max_norm), _p(clip))
