@@ -86,6 +86,114 @@ int dx_gemm(const dx_gemm_desc* d, void* stream);
 int dx_gemm_tc_debug(const dx_gemm_desc* d, int32_t block_n, int32_t stages, int32_t a_lbo, int32_t a_sbo,
                      int32_t b_lbo, int32_t b_sbo, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * T<->V axis re-layout fused with ScaleNorm bookkeeping.  src is [B,P,Q,d] (tokens (b,p)), dst is [B,Q,P,d].
+ *   fwd: dst[b,q,p,:] = src[b,p,q,:] * (sqrt(Q*d)*g[0]/||src row (b,p)||) + pos_bcast[q,p,:] + pos_batched[b,q,p,:];
+ *        dst_rowsq[b*Q+q] = ||dst row||^2.  src_rowsq==NULL: no scaling.  pos_* may be NULL.
+ *   bwd: dsrc = s*(gy - src*<src,gy>/||src||^2) with gy the transposed gdst; *dg += sum <gy,src>*c/||src||.
+ * Replaces: psi.transpose(1,2).flatten(2) + full_event_embedding.weight, event_outs.flatten(2) + time_embeddings
+ * (duett/duett.py:274-279; models/main_architecture_duett.py:71-91) and the x_transformers final/pre ScaleNorm
+ * reductions around them.  d % 8 == 0. */
+int dx_relayout_fwd(const void* src, const float* src_rowsq, const float* g, const float* pos_bcast,
+                    const void* pos_batched, void* dst, float* dst_rowsq, int B, int P, int Q, int d, int act_dtype,
+                    void* stream);
+int dx_relayout_bwd(const void* gdst, const void* src, const float* src_rowsq, const float* g, void* dsrc, float* dg,
+                    int B, int P, int Q, int d, int act_dtype, void* stream);
+
+/* out[n] (+)= sum_m X[m*ld+n]  — bias / positional-embedding gradients (autograd of nn.Linear bias, duett.py:275). */
+int dx_colsum(const void* X, int64_t ld, int M, int64_t N, float* out, int accumulate, int dtype, void* stream);
+/* y (+)= alpha*x over n elements (n % 8 == 0) — accumulation of per-layer time-embedding gradients. */
+int dx_axpy(const void* x, void* y, int64_t n, float alpha, int accumulate, int dtype, void* stream);
+/* dtype conversion of a dense buffer (fp32 master weights -> bf16 operands; autocast's casts). */
+int dx_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, void* stream);
+/* out[i] = c*g[0]/max(sqrt(rowsq[i]),1e-12): x_transformers ScaleNorm row scale (duett/duett.py:95-105). */
+int dx_scalenorm_scale(const float* rowsq, const float* g, float c, float* out, int N, void* stream);
+/* rowdot[n] = <a[n,:], g[n,:]>; g[n,:] *= row_scale[n] (ScaleNorm backward bookkeeping on [N,C] tensors). */
+int dx_rowdot_scale(const void* a, void* g, const float* row_scale, float* rowdot, int N, int C, int dtype, void* stream);
+/* sink[0] += sum(x)/g[0]: ScaleNorm gain gradient. */
+int dx_sum_div_acc(const float* x, int64_t n, const float* g, float* sink, void* stream);
+
+/* Unmasked multi-head attention core softmax(q k^T / sqrt(dh)) v, fp32 softmax.  Element (b,s,h,i) of a tensor lives at
+ * ptr + b*bs + s*rs + h*dh + i (strides in elements).  lse: [B,H,Sq] f32.  dh in {4,8,12,16,32,64,128}.
+ * Replaces: x_transformers Attention core (duett/duett.py:95-105 call sites :276,:279) and the nn.MultiheadAttention core
+ * of _PerceiverBlock (models/main_architecture_duett.py:752,759). */
+int dx_attn_fwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_rs, const void* v,
+                int64_t v_bs, int64_t v_rs, void* o, int64_t o_bs, int64_t o_rs, float* lse, int B, int H, int Sq, int Sk,
+                int dh, int dtype, void* stream);
+int dx_attn_bwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_rs, const void* v,
+                int64_t v_bs, int64_t v_rs, const void* o, int64_t o_bs, int64_t o_rs, const void* go, int64_t go_bs,
+                int64_t go_rs, void* dq, int64_t dq_bs, int64_t dq_rs, void* dk, int64_t dk_bs, int64_t dk_rs, void* dv,
+                int64_t dv_bs, int64_t dv_rs, const float* lse, float* D_ws, int B, int H, int Sq, int Sk, int dh,
+                int dtype, void* stream);
+
+/* Value/count embedding into psi[B,T+1,V+1,d]: count lookup (n_obs_embedding, clip 0..15), V grouped MLPs
+ * Linear(2,64)-ReLU-BatchNorm(batch stats over B*T)-Linear(64,d), static column, [REP] row, MASK substitution.
+ * xs: [B,T,2V+1] f32 (values | counts | masked-step flag).  Stacked parameters: W0 [V,64,2], b0/gamma/beta/run_* [V,64],
+ * W4 [V,d,64], b4 [V,d], nobs [16], special [8,d], tab [B,d] (tab_encoder output).  Saves mean/rstd [V,64].
+ * Replaces: duett/duett.py:245-266 == models/main_architecture_duett.py:31-65 (the per-variable Python loop). */
+int dx_embed_fwd(const float* xs, int B, int T, int V, int d, const float* W0, const float* b0, const float* gamma,
+                 const float* beta, float* run_mean, float* run_var, const float* W4, const float* b4, const float* nobs,
+                 const float* special, const float* tab, void* psi, int act_dtype, double* stats_ws, float* mean,
+                 float* rstd, int training, void* stream);
+/* Parameter gradients are accumulated (f32); dtab [B,d] is written.  dhn_ws [V,B*T,64] f32, dgb_ws [2,V,64] f32 scratch. */
+int dx_embed_bwd(const float* xs, int B, int T, int V, int d, const float* W0, const float* b0, const float* gamma,
+                 const float* beta, const float* W4, const float* nobs, const float* mean, const float* rstd,
+                 const void* dpsi, int act_dtype, float* dhn_ws, float* dgb_ws, float* dW0, float* db0, float* dgamma,
+                 float* dbeta, float* dW4, float* db4, float* dnobs, float* dspecial, float* dtab, int training,
+                 void* stream);
+
+/* BatchNormLastDim on [R,C] f32 (duett/duett.py:11-22; tab_encoder, cve, head) and LayerNorm on [R,C]
+ * (models/main_architecture_duett.py:745-774).  Backward accumulates dw/db; dx may be NULL. */
+int dx_bn2d_fwd(const float* x, int R, int C, const float* w, const float* b, float* run_mean, float* run_var, float* y,
+                float* mean, float* rstd, int training, void* stream);
+int dx_bn2d_bwd(const float* dy, const float* x, int R, int C, const float* w, const float* mean, const float* rstd,
+                float* dx, float* dw, float* db, int training, void* stream);
+int dx_layernorm_fwd(const void* x, int R, int C, const float* w, const float* b, void* y, float* mean, float* rstd,
+                     int dtype, void* stream);
+int dx_layernorm_bwd(const void* dy, const void* x, int R, int C, const float* w, const float* mean, const float* rstd,
+                     void* dx, float* dw, float* db, int dtype, void* stream);
+/* out = g * act'(aux), act in DX_ACT_{GELU,RELU,TANH}_BWD. */
+int dx_act_bwd(const void* g, const void* aux, void* out, int64_t n, int act, int dtype, void* stream);
+
+/* Pooling / gathers around the heads: mean over the T hourly tokens (models/main_architecture_duett.py:1228-1231,
+ * duett/duett.py:297-298); row / column gathers of the SSL heads (duett/duett.py:291-296,310-313) and their scatter. */
+int dx_mean_rows(const void* x, float* y, int B, int T1, int T, int64_t E, int dtype, void* stream);
+int dx_mean_rows_bwd(const float* dy, void* dx, int B, int T1, int T, int64_t E, int dtype, void* stream);
+int dx_gather_vec(const void* src, const int64_t* offsets, float* out, int n, int L, int dtype, void* stream);
+int dx_scatter_vec(const float* src, const int64_t* offsets, void* dst, int n, int L, int accumulate, int dtype, void* stream);
+
+/* Losses: each writes the scalar terms AND d(loss)/d(logits) (pass NULL to skip the gradient).
+ *  dx_kd_loss          out3 = {alpha*bce+(1-alpha)*kd, bce, kd}       loss/losses_duett.py:8-25,39-57
+ *  dx_bce_logits       mean_i w_i*bce(z_i,y_i), w = y>0 ? w_pos:w_neg  duett/duett.py:360-365
+ *  dx_masked_mse_bce   out2[0] += mse(yhat*m,y*m); out2[1] += w*bce(phat,m)   duett/duett.py:337-358
+ *  dx_masked_bce_cols  per[k] = sum_b bce*m/(sum_b m+eps); dz scaled by coef[k] (NULL=1)  loss/losses_duett.py:152-194
+ *  dx_aux_residual_kl  label-smoothed Bernoulli KL on sigmoid(img.detach()+corr)   training_duett/engine.py:149-165 */
+int dx_kd_loss(const float* zs, const float* zt, const float* y, int B, float T, float alpha, float pos_weight, float eps,
+               float* out3, float* dz, void* stream);
+int dx_bce_logits(const float* z, const float* y, int n, float w_pos, float w_neg, float* out, float* dz, void* stream);
+int dx_masked_mse_bce(const float* yhat, const float* phat, const float* y, const float* m, int n, float w_presence,
+                      float* out2, float* d_yhat, float* d_phat, void* stream);
+int dx_masked_bce_cols(const float* z, const float* y, const float* m, const float* pos_weight, const float* coef, int B,
+                       int K, float eps, float* per, float* dz, void* stream);
+int dx_aux_residual_kl(const float* img_logits, const float* scaled_corr, const float* y, const float* mask, int n,
+                       float eps_smooth, float* out, float* dcorr, void* stream);
+/* out[i] = x[i]*s[i % ns] (device-side scale by the upstream loss gradient; no host sync). */
+int dx_scale_dev(const float* x, const float* s, float* out, int64_t n, int ns, void* stream);
+/* Pathology-query logits (models/main_architecture_duett.py:631-639): img = hi+bias_i, ts = ht+bias_t, scaled = beta*corr,
+ * fusion = img.detach()+scaled; backward accumulates dbeta/dbias_*, writes d_corr. */
+int dx_fusion_logits(const float* hi, const float* ht, const float* corr, const float* bias_i, const float* bias_t,
+                     const float* beta, float* img, float* ts, float* scaled, float* fusion, int B, int K, void* stream);
+int dx_fusion_logits_bwd(const float* d_img, const float* d_ts, const float* d_scaled, const float* d_fus, const float* corr,
+                         const float* beta, float* d_corr, float* dbeta, float* dbias_i, float* dbias_t, int B, int K,
+                         void* stream);
+
+/* Fused AdamW on flat f32 buffers + global-norm clipping pieces (training_duett/trainer.py:383,902; duett/duett.py:325-327;
+ * duett/train_duett_ssl.py:191 gradient_clip_val).  Effective grad = g * grad_scale * (grad_scale_dev ? *grad_scale_dev : 1). */
+int dx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+             float weight_decay, int step, const float* grad_scale_dev, float grad_scale, void* stream);
+int dx_sumsq(const float* x, int64_t n, float* out, void* stream);
+int dx_clip_factor(const float* sumsq, float max_norm, float* clip, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,304 @@
+"""Per-kernel parity on a real B200: every CUDA kernel wrapper (through the C ABI of libduett_b200.so) against the
+torch contract in tests/ops_emulator.py, fp32 and bf16 storage.  Tolerances: fp32 1e-4 (re-association only; the
+north-star bound is 1e-3), bf16 2e-2 (north-star bound)."""
+import math
+
+import pytest
+import torch
+
+import ops_emulator as E
+
+pytestmark = pytest.mark.gpu
+
+DT = [torch.float32, torch.bfloat16]
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cpu(*ts):
+    return [None if t is None else t.detach().cpu().clone() for t in ts]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from multimodal_edema_prediction_b200 import ops as o
+    assert o.L.lib().dx_device_ok() == 1, "not an sm_100 device"
+    return o
+
+
+def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(dtype)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+def test_gemm_plain(ops, dt, a_mn, b_mn):
+    M, N, K = 520, 392, 264
+    a = rnd(*((K, M) if a_mn else (M, K)), dtype=dt, seed=1)
+    b = rnd(*((K, N) if b_mn else (N, K)), dtype=dt, seed=2)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm_(a, b, a_mn=a_mn, b_mn=b_mn, out=out)
+    ref = torch.empty(M, N)
+    E.gemm_(*cpu(a, b), a_mn=a_mn, b_mn=b_mn, out=ref)
+    assert rel(out, ref) < 1e-5      # fp32 accumulation of identical inputs
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_gemm_fused_epilogues(ops, dt):
+    M, N, K = 300, 264, 136
+    a, b = rnd(M, K, dtype=dt, seed=3), rnd(N, K, dtype=dt, seed=4, scale=0.1)
+    rs, rs2 = torch.rand(M, device="cuda") + 0.5, torch.rand(M, device="cuda") + 0.5
+    bias = rnd(N, seed=5)
+    res, aux, cx = rnd(M, N, dtype=dt, seed=6), rnd(M, N, dtype=dt, seed=7), rnd(M, N, dtype=dt, seed=8)
+    num, den = rnd(M, seed=9), torch.rand(M, device="cuda") + 1
+    cases = {
+        "ffn_in": dict(row_scale=rs, bias=bias, act=ops.ACT_GELU, want_out2=True),
+        "resid": dict(bias=bias, res=res, want_rowsq=True),
+        "dx": dict(res=res, cx=cx, coef_num=num, coef_den=den),
+        "gelu_bwd": dict(act=ops.ACT_GELU_BWD, aux=aux, aux_bias=bias, row_scale2=rs2, want_out2=True, want_rowdot=True),
+        "relu": dict(bias=bias, act=ops.ACT_RELU),
+        "tanh": dict(bias=bias, act=ops.ACT_TANH),
+    }
+    for name, kw in cases.items():
+        kw = dict(kw)
+        o2, rq, rd = kw.pop("want_out2", False), kw.pop("want_rowsq", False), kw.pop("want_rowdot", False)
+        out = torch.empty(M, N, device="cuda", dtype=dt)
+        out2 = torch.empty(M, N, device="cuda", dtype=dt) if o2 else None
+        rowsq = torch.zeros(M, device="cuda") if rq else None
+        rowdot = torch.zeros(M, device="cuda") if rd else None
+        ops.gemm_(a, b, out=out, out2=out2, row_sumsq=rowsq, row_dot=rowdot, act_dtype=dt, **kw)
+        r_out, r_out2 = torch.empty(M, N), (torch.empty(M, N) if o2 else None)
+        r_rowsq, r_rowdot = (torch.zeros(M) if rq else None), (torch.zeros(M) if rd else None)
+        ckw = {k: (v.detach().cpu() if torch.is_tensor(v) else v) for k, v in kw.items()}
+        E.gemm_(*cpu(a, b), out=r_out, out2=r_out2, row_sumsq=r_rowsq, row_dot=r_rowdot, **ckw)
+        assert rel(out, r_out) < TOL[dt], name
+        if o2:
+            assert rel(out2, r_out2) < TOL[dt], name
+        if rq:
+            assert rel(rowsq, r_rowsq) < 1e-4, name
+        if rd:
+            assert rel(rowdot, r_rowdot) < 1e-3, name
+
+
+def test_gemm_tc_matches_ffma_on_bf16(ops):
+    """The tcgen05 kernel and the FFMA kernel are independent implementations: same bf16 inputs, same fp32 result."""
+    M, N, K = 1000, 520, 1096
+    a, b = rnd(M, K, dtype=torch.bfloat16, seed=11), rnd(N, K, dtype=torch.bfloat16, seed=12)
+    o1 = torch.empty(M, N, device="cuda")
+    o2 = torch.empty(M, N, device="cuda")
+    ops.gemm_(a, b, out=o1)
+    ops.gemm_(a, b, out=o2, force_simt=True)
+    assert rel(o1, o2) < 1e-5
+    acc = torch.full((M, N), 2.0, device="cuda")
+    ops.gemm_(a, b, out=acc, accumulate=True)
+    assert rel(acc - 2.0, o1) < 1e-5
+
+
+def test_gemm_rejects_bad_arguments(ops):
+    a, b = rnd(64, 20, dtype=torch.bfloat16), rnd(32, 20, dtype=torch.bfloat16)     # lda = 20 is not 16 B aligned
+    with pytest.raises(ops.L.DxError):
+        ops.gemm_(a, b, out=torch.empty(64, 32, device="cuda"))
+    with pytest.raises(ops.L.DxError):
+        ops.gemm_(rnd(8, 4), rnd(8, 5), out=torch.empty(8, 8, device="cuda"))       # contraction mismatch
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_relayout_fwd_bwd(ops, dt):
+    B, P, Q, d = 3, 5, 7, 16
+    src = rnd(B, P, Q, d, dtype=dt, seed=20)
+    rowsq = (src.float() ** 2).sum((2, 3)).reshape(-1).contiguous()
+    g = torch.tensor([1.3], device="cuda")
+    pos_b, pos_n = rnd(Q, P * d, seed=21), rnd(B, Q, P * d, dtype=dt, seed=22)
+    for kw in (dict(), dict(src_rowsq=rowsq, g=g, pos_bcast=pos_b), dict(src_rowsq=rowsq, g=g, pos_batched=pos_n)):
+        dst, rq = ops.relayout_fwd(src, B, P, Q, d, **kw)
+        ckw = {k: v.cpu() for k, v in kw.items()}
+        rdst, rrq = E.relayout_fwd(src.cpu(), B, P, Q, d, **ckw)
+        assert rel(dst, rdst) < TOL[dt] and rel(rq, rrq) < TOL[dt]
+    gd = rnd(B, Q, P, d, dtype=dt, seed=23)
+    dg = torch.zeros(1, device="cuda")
+    ds = ops.relayout_bwd(gd, B, P, Q, d, src=src, src_rowsq=rowsq, g=g, dg=dg)
+    rdg = torch.zeros(1)
+    rds = E.relayout_bwd(gd.cpu(), B, P, Q, d, src=src.cpu(), src_rowsq=rowsq.cpu(), g=g.cpu(), dg=rdg)
+    assert rel(ds, rds) < TOL[dt] and rel(dg, rdg) < TOL[dt]
+    assert rel(ops.relayout_bwd(gd, B, P, Q, d), E.relayout_bwd(gd.cpu(), B, P, Q, d)) == 0.0     # pure permutation: exact
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("S,D,H", [(129, 128, 2), (33, 64, 2), (5, 8, 2), (35, 24, 2), (70, 256, 2)])
+def test_attention_fwd_bwd(ops, dt, S, D, H):
+    B = 3
+    qkv = rnd(B, S, 3 * D, dtype=dt, seed=30, scale=0.7)
+    q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    o, lse = ops.attn_fwd(q, k, v, H)
+    ro, rlse = E.attn_fwd(*cpu(q, k, v), H)
+    assert rel(o, ro) < TOL[dt] and rel(lse, rlse) < 1e-3
+    go = rnd(B, S, D, dtype=dt, seed=31)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(q, k, v, o, go, lse, H, dqkv[:, :, :D], dqkv[:, :, D:2 * D], dqkv[:, :, 2 * D:])
+    rq, rk, rv = torch.empty(B, S, D), torch.empty(B, S, D), torch.empty(B, S, D)
+    E.attn_bwd(*cpu(q, k, v, o, go, lse), H, rq, rk, rv)
+    assert rel(dqkv, torch.cat([rq, rk, rv], 2)) < TOL[dt]
+
+
+def test_cross_attention_few_queries(ops):
+    B, Sq, Sk, D, H = 2, 7, 200, 256, 4
+    q, k, v = rnd(B, Sq, D, seed=33), rnd(B, Sk, D, seed=34), rnd(B, Sk, D, seed=35)
+    o, lse = ops.attn_fwd(q, k, v, H)
+    ro, _ = E.attn_fwd(*cpu(q, k, v), H)
+    assert rel(o, ro) < 1e-4
+    go = rnd(B, Sq, D, seed=36)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ops.attn_bwd(q, k, v, o, go, lse, H, dq, dk, dv)
+    rq, rk, rv = torch.empty(B, Sq, D), torch.empty(B, Sk, D), torch.empty(B, Sk, D)
+    E.attn_bwd(*cpu(q, k, v, o, go, lse), H, rq, rk, rv)
+    assert rel(dq, rq) < 1e-4 and rel(dk, rk) < 1e-4 and rel(dv, rv) < 1e-4
+
+
+def _embed_inputs(B, T, V, d, seed=40, ssl=True):
+    g = torch.Generator().manual_seed(seed)
+    obs = (torch.rand(B, T, V, generator=g) < 0.3).float()
+    xs = torch.cat((torch.randn(B, T, V, generator=g) * obs, obs * torch.randint(1, 20, (B, T, V), generator=g).float(),
+                    torch.zeros(B, T, 1)), 2)
+    if ssl:
+        for b in range(B):
+            xs[b, b % T, :] = 0; xs[b, b % T, -1] = 1
+            xs[b, :, (3 * b) % V] = 0; xs[b, :, V + (3 * b) % V] = -1
+    P = dict(W0=torch.randn(V, 64, 2, generator=g) * 0.7, b0=torch.randn(V, 64, generator=g) * 0.3,
+             gamma=1 + 0.1 * torch.randn(V, 64, generator=g), beta=0.1 * torch.randn(V, 64, generator=g),
+             W4=torch.randn(V, d, 64, generator=g) * 0.12, b4=torch.randn(V, d, generator=g) * 0.1,
+             nobs=torch.randn(16, generator=g), special=torch.randn(8, d, generator=g), tab=torch.randn(B, d, generator=g))
+    return xs, P
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,T,V,d", [(6, 4, 5, 8), (16, 32, 34, 24), (8, 24, 40, 128)])
+def test_embedding_fwd_bwd(ops, dt, B, T, V, d):
+    xs, P = _embed_inputs(B, T, V, d)
+    c = lambda t: t.cuda().contiguous()
+    for training in (True, False):
+        rm, rv = torch.zeros(V, 64) + 0.05, torch.ones(V, 64) * 0.9
+        rmc, rvc = c(rm), c(rv)
+        psi, mean, rstd = ops.embed_fwd(c(xs), V, d, c(P["W0"]), c(P["b0"]), c(P["gamma"]), c(P["beta"]), rmc, rvc, c(P["W4"]),
+                                        c(P["b4"]), c(P["nobs"]), c(P["special"]), c(P["tab"]), dt, training)
+        rpsi, rmean, rrstd = E.embed_fwd(xs, V, d, P["W0"], P["b0"], P["gamma"], P["beta"], rm, rv, P["W4"], P["b4"], P["nobs"],
+                                         P["special"], P["tab"], dt, training)
+        assert rel(psi, rpsi) < TOL[dt], training
+        assert rel(mean, rmean) < 1e-4 and rel(rstd, rrstd) < 1e-3
+        assert rel(rmc, rm) < 1e-4 and rel(rvc, rv) < 1e-3                      # running statistics
+        dpsi = rnd(B, T + 1, V + 1, d, dtype=dt, seed=41)
+        names = dict(dW0=P["W0"], db0=P["b0"], dgamma=P["gamma"], dbeta=P["beta"], dW4=P["W4"], db4=P["b4"], dnobs=P["nobs"],
+                     dspecial=P["special"])
+        G = {k: torch.zeros_like(v).cuda() for k, v in names.items()}
+        RG = {k: torch.zeros_like(v) for k, v in names.items()}
+        dtab = ops.embed_bwd(c(xs), V, d, c(P["W0"]), c(P["b0"]), c(P["gamma"]), c(P["beta"]), c(P["W4"]), c(P["nobs"]), mean, rstd,
+                             dpsi, G, training)
+        rdtab = E.embed_bwd(xs, V, d, P["W0"], P["b0"], P["gamma"], P["beta"], P["W4"], P["nobs"], rmean, rrstd, dpsi.cpu(), RG,
+                            training)
+        assert rel(dtab, rdtab) < TOL[dt]
+        for k in G:
+            assert rel(G[k], RG[k]) < (5e-4 if dt == torch.float32 else 2e-2), (k, training)
+
+
+def test_norm_kernels(ops):
+    R, C = 300, 90
+    x, w, b = rnd(R, C, seed=50), rnd(C, seed=51), rnd(C, seed=52)
+    for training in (True, False):
+        rm, rv = torch.zeros(C, device="cuda") + 0.1, torch.ones(C, device="cuda")
+        crm, crv = rm.cpu().clone(), rv.cpu().clone()
+        y, mean, rstd = ops.bn2d_fwd(x, w, b, rm, rv, training)
+        ry, rmean, rrstd = E.bn2d_fwd(x.cpu(), w.cpu(), b.cpu(), crm, crv, training)
+        assert rel(y, ry) < 1e-4 and rel(rm, crm) < 1e-5 and rel(rv, crv) < 1e-4
+        dy = rnd(R, C, seed=53)
+        dw, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        dx = ops.bn2d_bwd(dy, x, w, mean, rstd, dw, db, training)
+        rdw, rdb = torch.zeros(C), torch.zeros(C)
+        rdx = E.bn2d_bwd(dy.cpu(), x.cpu(), w.cpu(), rmean, rrstd, rdw, rdb, training)
+        assert rel(dx, rdx) < 1e-4 and rel(dw, rdw) < 1e-4 and rel(db, rdb) < 1e-4
+    for dt in DT:
+        x = rnd(500, 256, dtype=dt, seed=54)
+        w, b = rnd(256, seed=55), rnd(256, seed=56)
+        y, mean, rstd = ops.layernorm_fwd(x, w, b)
+        ry, rmean, rrstd = E.layernorm_fwd(x.cpu(), w.cpu(), b.cpu())
+        assert rel(y, ry) < TOL[dt]
+        dy = rnd(500, 256, dtype=dt, seed=57)
+        dw, db = torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda")
+        dx = ops.layernorm_bwd(dy, x, w, mean, rstd, dw, db)
+        rdw, rdb = torch.zeros(256), torch.zeros(256)
+        rdx = E.layernorm_bwd(dy.cpu(), x.cpu(), w.cpu(), rmean, rrstd, rdw, rdb)
+        assert rel(dx, rdx) < TOL[dt] and rel(dw, rdw) < TOL[dt] and rel(db, rdb) < TOL[dt]
+
+
+def test_small_kernels(ops):
+    x = rnd(37, 1000, dtype=torch.bfloat16, seed=60)
+    out = torch.zeros(1000, device="cuda")
+    ops.colsum(x, out, accumulate=True)
+    assert rel(out, x.float().sum(0)) < 1e-5
+    x3 = rnd(4, 9, 64, dtype=torch.bfloat16, seed=61)
+    assert rel(ops.mean_rows(x3, 8), E.mean_rows(x3.cpu(), 8)) < 1e-6
+    dy = rnd(4, 64, seed=62)
+    assert rel(ops.mean_rows_bwd(dy, 9, 8, torch.float32), E.mean_rows_bwd(dy.cpu(), 9, 8, torch.float32)) < 1e-6
+    off = torch.tensor([0, 128, 320], device="cuda")
+    assert torch.equal(ops.gather_vec(x3, off, 64).cpu(), E.gather_vec(x3.cpu(), off.cpu(), 64))
+    g, aux = rnd(100, 40, seed=63), rnd(100, 40, seed=64)
+    for code in (E.ACT_GELU_BWD, E.ACT_RELU_BWD, E.ACT_TANH_BWD):
+        assert rel(ops.act_bwd(g, aux, code), E.act_bwd(g.cpu(), aux.cpu(), code)) < 1e-5
+    rowsq, gg = torch.rand(50, device="cuda") + 0.1, torch.tensor([0.7], device="cuda")
+    assert rel(ops.scalenorm_scale(rowsq, gg, 96), E.scalenorm_scale(rowsq.cpu(), gg.cpu(), 96)) < 1e-6
+    a, gr = rnd(50, 24, seed=65), rnd(50, 24, seed=66)
+    gr2 = gr.clone()
+    rd = ops.rowdot_scale(a, gr2, rowsq)
+    cgr = gr.cpu().clone()
+    rrd = E.rowdot_scale(a.cpu(), cgr, rowsq.cpu())
+    assert rel(rd, rrd) < 1e-5 and rel(gr2, cgr) < 1e-6
+
+
+def test_loss_kernels(ops):
+    B, K = 37, 7
+    g = torch.Generator().manual_seed(70)
+    zs, zt = torch.randn(B, generator=g) * 2, torch.randn(B, generator=g) * 2
+    y = (torch.rand(B, generator=g) < 0.3).float()
+    for pw in (None, 2.5):
+        out, dz = ops.kd_loss(zs.cuda(), zt.cuda(), y.cuda(), 4.0, 0.5, pw)
+        rout, rdz = E.kd_loss(zs, zt, y, 4.0, 0.5, pw)
+        assert rel(out, rout) < 1e-5 and rel(dz, rdz) < 1e-4
+    out, dz = ops.bce_logits(zs.cuda(), y.cuda(), 1.7, 0.6)
+    rout, rdz = E.bce_logits(zs, y, 1.7, 0.6)
+    assert rel(out, rout) < 1e-5 and rel(dz, rdz) < 1e-5
+    yh, ph, yy = torch.randn(B, K, generator=g), torch.randn(B, K, generator=g), torch.randn(B, K, generator=g)
+    m = (torch.rand(B, K, generator=g) < 0.4).float()
+    o2, ro2 = torch.zeros(2, device="cuda"), torch.zeros(2)
+    d1, d2 = ops.masked_mse_bce(yh.cuda(), ph.cuda(), yy.cuda(), m.cuda(), 0.2, o2)
+    r1, r2 = E.masked_mse_bce(yh, ph, yy, m, 0.2, ro2)
+    assert rel(o2, ro2) < 1e-5 and rel(d1, r1) < 1e-5 and rel(d2, r2) < 1e-5
+    pwv = torch.rand(K, generator=g) + 1
+    per, dz = ops.masked_bce_cols(yh.cuda(), y[:, None].expand(B, K).contiguous().cuda(), m.cuda(), pwv.cuda(), None, 1e-6)
+    rper, rdz = E.masked_bce_cols(yh, y[:, None].expand(B, K).contiguous(), m, pwv, None, 1e-6)
+    assert rel(per, rper) < 1e-5 and rel(dz, rdz) < 1e-5
+    ym = (torch.rand(B, K, generator=g) < 0.2).float()
+    out, dc = ops.aux_residual_kl(yh.cuda(), ph.cuda(), ym.cuda(), m.cuda(), 0.05)
+    rout, rdc = E.aux_residual_kl(yh, ph, ym, m, 0.05)
+    assert rel(out, rout) < 1e-5 and rel(dc, rdc) < 1e-4
+
+
+def test_adamw_matches_torch(ops):
+    n = 10007
+    p = rnd(n, seed=80); g = rnd(n, seed=81)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        ref.grad = g.clone() * step
+        opt.step()
+        ops.adamw(p, g * step, m, v, 1e-3, (0.9, 0.999), 1e-8, 0.05, step)
+    assert rel(p, ref) < 1e-6
+    ss = torch.zeros(1, device="cuda")
+    ops.sumsq(g, ss)
+    assert rel(ss, (g * g).sum()) < 1e-5
+    clip = torch.zeros(1, device="cuda")
+    ops.clip_factor(ss, 1.0, clip)
+    assert rel(clip, torch.clamp(1.0 / (g.norm() + 1e-6), max=1.0)) < 1e-5

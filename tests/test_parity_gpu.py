@@ -1,0 +1,245 @@
+"""End-to-end parity on a real B200 (through the reference-facing nn.Module API -> C ABI -> CUDA kernels):
+
+  * replay of the golden fixtures generated from the REFERENCE'S OWN FILES (tests/golden, oracle/make_golden.py):
+    logits, every loss term and every parameter gradient — fp32 mode within 1e-3 relative (north-star bound),
+    bf16 mode within 2e-2;
+  * a MIMIC-shaped and a C1-shaped (BASELINE.json config 1, reduced batch) random problem against the CPU oracle;
+  * AUROC on a fixed synthetic eval set, scored like training_duett/evaluator.py:10-37 (sigmoid -> sklearn).
+Relative error is ||a-b||2/||b||2 per tensor (SURVEY §7 "error metric"); cancellation-dominated gradients get an
+absolute floor tied to the largest gradient entry, stated in `_grad_check`.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import golden_cfg, load, rel
+from oracle import duett_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(d_static_num=3, d_time_series_num=5, d_target=1, d_embedding=8, masked_transform_timesteps=4, max_len=4,
+          n_duett_layers=2, d_feedforward=96)
+MODES = [("fp32", 1e-3), ("bf16", 2e-2)]
+
+
+def dev(t):
+    return t.cuda() if torch.is_tensor(t) else t
+
+
+def _ref_keyed_grads(module):
+    from multimodal_edema_prediction_b200 import state_keys
+    from multimodal_edema_prediction_b200.duett.duett import Model
+    sd = {n: (p.grad if p.grad is not None else torch.zeros_like(p)).detach().cpu() for n, p in module.named_parameters()}
+    for name, m in module.named_modules():
+        if isinstance(m, Model):
+            state_keys.to_reference(sd, name + "." if name else "")
+    return sd
+
+
+def _grad_check(got, want, tol, floor=1e-3):
+    """per tensor: ||got-want|| <= tol*||want|| + floor*tol*max|grad|*sqrt(numel)."""
+    bad = []
+    gscale = max(float(v.abs().max()) for v in want.values())
+    for k, w in want.items():
+        g = got.get(k)
+        if g is None:
+            bad.append((k, "missing")); continue
+        if (g.double() - w.double()).norm() > tol * w.double().norm() + floor * tol * gscale * w.numel() ** 0.5 + 1e-7:
+            bad.append((k, rel(g, w), float(w.abs().max())))
+    assert not bad, (len(bad), bad[:10])
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_golden_student_kd(mode, tol):
+    from multimodal_edema_prediction_b200.loss.losses_duett import StudentKDLoss
+    from multimodal_edema_prediction_b200.models.main_architecture_duett import DuettFeatureExtractor, StudentModel
+    G = load("g1_student_kd")
+    duett = DuettFeatureExtractor(pretrain=False, precision=mode, **KW)
+    student = StudentModel(duett, pool="mean", head_hidden=16, head_dropout=0.0)
+    student.load_state_dict(G["param"], strict=True)
+    student.cuda().train()
+    I = G["in"]
+    x_ts, x_static, bin_ends = tuple(I["x_ts"]), tuple(I["x_static"]), list(I["bin_ends"])
+    tokens = duett.encode(duett.feats_to_input((x_ts, x_static, bin_ends), 6))
+    assert rel(tokens.float().cpu(), G["out"]["tokens"]) < tol
+    student.load_state_dict(G["param"])
+    z_s = student(x_ts, x_static, bin_ends)
+    assert rel(z_s.cpu(), G["out"]["z_s"]) < tol * 3            # logits ~0.1 in magnitude: bf16 noise is relatively larger
+    losses = StudentKDLoss(kd_T=4.0, kd_alpha=0.5, pos_weight=2.0)(z_s, dev(I["z_t"]), dev(I["y"]))
+    for k in ("total", "bce", "kd"):
+        assert rel(losses[k].cpu(), G["out"][k]) < tol, k
+    losses["total"].backward()
+    _grad_check(_ref_keyed_grads(student), G["grad"], tol * (1 if mode == "fp32" else 2.5))
+    if mode == "fp32":
+        sd = student.state_dict()
+        for k, want in G["after"].items():
+            got = sd[k].cpu()
+            assert torch.equal(got, want) if want.dtype == torch.long else (rel(got, want) < 1e-4 or (got - want).abs().max() < 1e-6), k
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_golden_supervised_ragged(mode, tol):
+    from multimodal_edema_prediction_b200.duett.duett import Model
+    G = load("g2_supervised")
+    model = Model(pretrain=False, fusion_method="rep_token", pos_frac=0.3, precision=mode, **KW)
+    model.load_state_dict(G["param"], strict=True)
+    model.cuda().train()
+    I = G["in"]
+    lens = I["n_timesteps"].tolist()
+    x_ts = tuple(I["xs_ts"][i, :n, :-1] for i, n in enumerate(lens))
+    times = [I["xs_times"][i, :n] for i, n in enumerate(lens)]
+    loss = model.training_step(((x_ts, tuple(I["xs_static"]), times), tuple(I["y"].tolist())), 0)
+    assert loss.dtype == torch.float64 and rel(loss.cpu(), G["out"]["loss"]) < tol
+    loss.backward()
+    _grad_check(_ref_keyed_grads(model), G["grad"], tol * (1 if mode == "fp32" else 2.5), floor=5e-2)
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_golden_ssl(mode, tol):
+    from multimodal_edema_prediction_b200.duett.duett import Model
+    G = load("g3_ssl")
+    model = Model(pretrain=True, seed=42, precision=mode, **KW)
+    model.load_state_dict(G["param"], strict=True)
+    model.cuda().train()
+    I = G["in"]
+    x = (tuple(I["x_ts"]), tuple(I["x_static"]), list(I["bin_ends"]))
+    x_pre, y, mask, y_ev, y_ev_mask = model.pretrain_prep_batch(x, 6)
+    assert torch.equal(x_pre[1].cpu(), G["out"]["xs_ts_clipped"])       # index / mask work: bit-exact
+    assert torch.equal(y.cpu(), G["out"]["y"]) and torch.equal(mask.cpu(), G["out"]["mask"])
+    assert torch.equal(y_ev.cpu(), G["out"]["y_events"]) and torch.equal(y_ev_mask.cpu(), G["out"]["y_events_mask"])
+    model.rng = np.random.default_rng(42)
+    outs = model.forward(x_pre, pretrain=True)
+    for got, key in zip(outs, ("y_hat_value", "y_hat_presence", "y_hat_events", "y_hat_events_presence")):
+        assert rel(got.cpu(), G["out"][key]) < tol * 2, key
+    model.load_state_dict(G["param"])
+    model.cuda()
+    loss = model.training_step((x, tuple([0.0] * 6)), 0)
+    assert rel(loss.cpu(), G["out"]["loss"]) < tol
+    loss.backward()
+    _grad_check(_ref_keyed_grads(model), G["grad"], tol * (1 if mode == "fp32" else 2.5))
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_golden_teacher_patch_dual(mode, tol):
+    from multimodal_edema_prediction_b200.loss.losses_duett import DualPathologyLoss
+    from multimodal_edema_prediction_b200.models.main_architecture_duett import (DuettFeatureExtractor,
+                                                                                 PatchDualPathologyPerceiver, TeacherModel)
+    from multimodal_edema_prediction_b200.training_duett import engine
+    G = load("g4_teacher")
+
+    class StubCXR(torch.nn.Module):
+        d_out = 16
+        def forward(self, pv):
+            return pv[:, 0], pv[:, 1:]
+
+    duett = DuettFeatureExtractor(pretrain=False, precision=mode, **KW)
+    perceiver = PatchDualPathologyPerceiver(7, duett.d_representation, d_latent=32, n_heads=4, dropout=0.0, head_hidden=16,
+                                            head_dropout=0.0)
+    teacher = TeacherModel(duett, StubCXR(), perceiver, patch_dual_pathology_mode=True, d_img=16)
+    teacher.load_state_dict(G["param"], strict=True)
+    teacher.cuda()
+    I = G["in"]
+    loss_fn = DualPathologyLoss(I["label_weights"], I["pos_weight"], 0.5, 0.5, 1.0).cuda()
+    opt = torch.optim.SGD(teacher.parameters(), lr=0.0)
+    batch = {"x_ts": tuple(I["x_ts"]), "x_static": tuple(I["x_static"]), "bin_ends": tuple(I["bin_ends"]),
+             "y": torch.zeros(6), "pixel_values": I["pixel_values"], "y_multi": I["y_multi"], "y_multi_mask": I["y_multi_mask"]}
+    res = engine.train_teacher_dual_pathology_batch(batch, teacher, loss_fn, opt, torch.device("cuda"), aux_residual_alpha=0.3)
+    assert abs(res["loss"] - float(G["out"]["loss"])) < tol * abs(float(G["out"]["loss"]))
+    for k in ("main_logit", "img_logits", "ts_logits", "fusion_logits"):
+        assert rel(res[k].cpu(), G["out"][k]) < tol * 2, k
+    for k in ("img_per", "ts_per", "fus_per"):
+        assert rel(res[k], G["out"][k]) < tol, k
+    _grad_check(_ref_keyed_grads(teacher), G["grad"], tol * (1 if mode == "fp32" else 2.5), floor=5e-2)
+
+
+def _oracle_vs_cuda_student(cfg, B, mode, tol, seed=0, pool="mean"):
+    from multimodal_edema_prediction_b200.models.main_architecture_duett import DuettFeatureExtractor, StudentModel
+    P = O.init_params(cfg, seed=seed)
+    H = O.init_student_head(cfg, seed=seed + 1)
+    batch = O.synth_batch(cfg, B, seed=1234 + seed)
+    x_static, xs_ts, xs_times, _ = O.feats_to_input(batch["x_ts"], batch["x_static"], batch["bin_ends"], cfg.T)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    Pl = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P.items()}
+    Hl = {k: v.clone().requires_grad_(True) for k, v in H.items()}
+    tokens_ref = O.encode(Pl, cfg, x_static, xs_ts, xs_times, training=True)
+    z_ref = O.student_forward(Pl, Hl, cfg, x_static, xs_ts, xs_times, pool=pool)
+    z_t = torch.randn(B, generator=torch.Generator().manual_seed(5)) * 1.5
+    L_ref = O.student_kd_loss(z_ref, z_t, batch["y"], 4.0, 0.5, None)
+    L_ref["total"].backward()
+    duett = DuettFeatureExtractor(cfg.d_static_num, cfg.V, 1, d_embedding=cfg.d_embedding, n_duett_layers=cfg.n_layers,
+                                  masked_transform_timesteps=cfg.T, max_len=cfg.T, d_feedforward=cfg.d_feedforward,
+                                  pretrain=False, precision=mode)
+    student = StudentModel(duett, pool=pool, head_hidden=128, head_dropout=0.0)
+    sd = {"duett." + k: v for k, v in P.items()}
+    sd.update({k: v for k, v in H.items()})
+    student.load_state_dict(sd, strict=True)
+    student.cuda().train()
+    from multimodal_edema_prediction_b200.loss.losses_duett import StudentKDLoss
+    x = (batch["x_ts"], batch["x_static"], list(batch["bin_ends"]))
+    tokens = duett.encode(duett.feats_to_input(x, B))
+    assert rel(tokens.float().cpu(), tokens_ref) < tol
+    student.load_state_dict(sd)
+    student.cuda()
+    z = student(*x)
+    losses = StudentKDLoss(kd_T=4.0, kd_alpha=0.5)(z, z_t.cuda(), batch["y"].cuda())
+    assert rel(z.cpu(), z_ref) < tol * 3
+    assert rel(losses["total"].cpu(), L_ref["total"]) < tol
+    losses["total"].backward()
+    want = {"duett." + k: v.grad for k, v in Pl.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    want.update({k: v.grad for k, v in Hl.items()})
+    got = _ref_keyed_grads(student)
+    _grad_check({k: got[k] for k in want}, want, tol * (1 if mode == "fp32" else 2.5), floor=5e-2)
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_mimic_default_shape_vs_oracle(mode, tol):
+    """The reference's real working point: S=24, V=34, T=24, d=24, L=2, F=512 (E=600, E'=840: exercises K tails,
+    non-multiple-of-64 widths and the padded time-embedding hidden (h=28))."""
+    cfg = O.DuettConfig(d_static_num=24, d_time_series_num=34, n_timesteps=24, d_embedding=24, n_layers=2)
+    _oracle_vs_cuda_student(cfg, B=16, mode=mode, tol=tol)
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_c1_shape_vs_oracle(mode, tol):
+    """BASELINE.json config 1 model (d=64, 2+2 layers, T=32, V=128) at a reduced batch so the CPU oracle takes seconds."""
+    cfg = O.DuettConfig(d_static_num=24, d_time_series_num=128, n_timesteps=32, d_embedding=64, n_layers=2)
+    _oracle_vs_cuda_student(cfg, B=4, mode=mode, tol=tol, seed=3, pool="rep_token")
+
+
+@pytest.mark.parametrize("mode,dauc", [("fp32", 1e-4), ("bf16", 5e-3)])
+def test_auroc_on_fixed_synthetic_eval_set(mode, dauc):
+    """evaluate_binary semantics (training_duett/evaluator.py:10-37): eval-mode logits -> sigmoid -> sklearn AUROC, one
+    process scoring the whole fixed set (seed 999)."""
+    from sklearn.metrics import roc_auc_score
+    from multimodal_edema_prediction_b200.models.main_architecture_duett import DuettFeatureExtractor, StudentModel
+    cfg = O.DuettConfig(d_static_num=24, d_time_series_num=34, n_timesteps=24, d_embedding=24, n_layers=2)
+    P, H = O.init_params(cfg, seed=7), O.init_student_head(cfg, seed=8)
+    H["head.3.weight"] = H["head.3.weight"] * 40.0       # O(1) logits so ranking is meaningful
+    for k in P:                                           # non-trivial running statistics for eval-mode BatchNorm
+        if k.endswith("running_mean"):
+            P[k] = 0.05 * torch.randn(P[k].shape, generator=torch.Generator().manual_seed(1))
+        if k.endswith("running_var"):
+            P[k] = 0.5 + torch.rand(P[k].shape, generator=torch.Generator().manual_seed(2))
+    N, bs = 1024, 256
+    data = O.synth_batch(cfg, N, seed=999)
+    duett = DuettFeatureExtractor(24, 34, 1, d_embedding=24, n_duett_layers=2, masked_transform_timesteps=24, max_len=24,
+                                  pretrain=False, precision=mode)
+    student = StudentModel(duett, pool="mean", head_dropout=0.0)
+    sd = {"duett." + k: v for k, v in P.items()}
+    sd.update(H)
+    student.load_state_dict(sd, strict=True)
+    student.cuda().eval()
+    zs, zr = [], []
+    with torch.no_grad():
+        for i in range(0, N, bs):
+            sl = slice(i, i + bs)
+            x = (data["x_ts"][sl], data["x_static"][sl], list(data["bin_ends"][sl]))
+            zs.append(student(*x).float().cpu())
+            xs, xt, tm, _ = O.feats_to_input(*x, cfg.T)
+            zr.append(O.student_forward(P, H, cfg, xs, xt, tm, pool="mean", training=False))
+    zs, zr = torch.cat(zs), torch.cat(zr)
+    y = (zr + torch.randn(N, generator=torch.Generator().manual_seed(3)) * zr.std() > zr.median()).float().numpy()
+    a_cuda = roc_auc_score(y, torch.sigmoid(zs).numpy())
+    a_ref = roc_auc_score(y, torch.sigmoid(zr).numpy())
+    assert abs(a_cuda - a_ref) < dauc, (a_cuda, a_ref)
+    assert rel(zs, zr) < (1e-3 if mode == "fp32" else 3e-2)
