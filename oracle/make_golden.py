@@ -35,6 +35,20 @@ def grads_of(module, prefix="grad/"):
     return {prefix + k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in module.named_parameters()}
 
 
+def self_dev(module, blobs, step_fn):
+    """How far the REFERENCE'S OWN bf16-autocast run lands from its own fp32 run on this fixture (global relative L2
+    over all parameter gradients, and the loss).  The bf16-mode parity tests bound the CUDA path's deviation by this."""
+    module.load_state_dict({k[len("param/"):]: v for k, v in blobs.items() if k.startswith("param/")})
+    module.zero_grad()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        loss = step_fn()
+    loss.backward()
+    got = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten().double()
+                     for _, p in module.named_parameters()])
+    want = torch.cat([blobs["grad/" + n].flatten().double() for n, _ in module.named_parameters()])
+    return {"selfdev/global_grad": (got - want).norm() / want.norm(), "selfdev/loss_bf16": loss.detach().double()}
+
+
 def params_of(module, prefix="param/"):
     return {prefix + k: v.clone() for k, v in module.state_dict().items()}
 
@@ -72,6 +86,8 @@ def main():
                   "in/bin_ends": torch.stack(batch["bin_ends"]), "in/y": batch["y"], "in/z_t": z_t,
                   "out/tokens": tokens, "out/z_s": z_s, "out/total": losses["total"], "out/bce": losses["bce"],
                   "out/kd": losses["kd"]})
+    blobs.update(self_dev(student, blobs, lambda: StudentKDLoss(kd_T=4.0, kd_alpha=0.5, pos_weight=2.0)(
+        student(batch["x_ts"], batch["x_static"], list(batch["bin_ends"])), z_t, batch["y"])["total"]))
     save("g1_student_kd", blobs)
 
     # ---- G2: supervised Lightning step (Model.training_step, pretrain=False, rep_token, pos_frac) -----------------
@@ -96,6 +112,8 @@ def main():
     blobs.update(grads_of(model))
     blobs.update({"in/xs_static": xin[0], "in/xs_ts": xin[1], "in/xs_times": xin[2],
                   "in/n_timesteps": np.array(xin[3]), "in/y": batch["y"], "out/y_hat": y_hat, "out/loss": loss})
+    blobs.update(self_dev(model, blobs, lambda: model.training_step(
+        ((tuple(t.clone() for t in x_ts), batch["x_static"], [t.clone() for t in times]), tuple(batch["y"].tolist())), 0)))
     save("g2_supervised", blobs)
 
     # ---- G3: SSL step (pretrain_prep_batch with numpy RNG seed 42 + forward(pretrain=True) + loss) ----------------
@@ -118,6 +136,10 @@ def main():
                   "out/mask": mask, "out/y_events": y_events, "out/y_events_mask": y_events_mask,
                   "out/y_hat_value": outs[0], "out/y_hat_presence": outs[1], "out/y_hat_events": outs[2],
                   "out/y_hat_events_presence": outs[3], "out/loss": loss})
+    def _ssl_step():
+        model.rng = np.random.default_rng(42)
+        return model.training_step((x, tuple(batch["y"].tolist())), 0)
+    blobs.update(self_dev(model, blobs, _ssl_step))
     save("g3_ssl", blobs)
 
     # ---- G4: teacher patch_dual step (TeacherModel + PatchDualPathologyPerceiver + DualPathologyLoss + aux KL) ------
@@ -165,6 +187,11 @@ def main():
         blobs["out/" + k] = out[k]
     for k in ("img_per", "ts_per", "fus_per", "img_total", "ts_total", "fus_total"):
         blobs["out/" + k] = losses[k]
+    def _teacher_step():
+        o = teacher(batch["x_ts"], batch["x_static"], list(batch["bin_ends"]), pv)
+        l = loss_fn(o["img_logits"].float(), o["ts_logits"].float(), o["fusion_logits"].float(), y_multi, y_mask)
+        return l["total"] + 0.3 * O.aux_residual_kl(o["img_logits"].float(), o["scaled_correction"].float(), y_multi, y_mask)
+    blobs.update(self_dev(teacher, blobs, _teacher_step))
     save("g4_teacher", blobs)
 
 

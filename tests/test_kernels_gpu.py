@@ -201,7 +201,7 @@ def test_embedding_fwd_bwd(ops, dt, B, T, V, d):
                             training)
         assert rel(dtab, rdtab) < TOL[dt]
         for k in G:
-            assert rel(G[k], RG[k]) < (5e-4 if dt == torch.float32 else 2e-2), (k, training)
+            assert rel(G[k], RG[k]) < (2e-3 if dt == torch.float32 else 2e-2), (k, training)   # fp32: atomics re-association
 
 
 def test_norm_kernels(ops):
