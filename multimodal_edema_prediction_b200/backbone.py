@@ -27,6 +27,10 @@ from .functional import BatchNorm2dFn, grad_sink, linear
 
 ENC_KEYS = ("g_attn", "wqkv", "wo", "g_ff", "w1", "b1", "w2", "b2", "g_final")
 
+# Set by ddp.GradReducer: called as hook("time_transformers.3") etc. from inside the backward as soon as an encoder's
+# parameter gradients are final, so its all-reduce bucket can start while the earlier layers are still running.
+GRAD_READY_HOOK = None
+
 
 class EncoderCtx:
     """Saved activations of one Encoder forward."""
@@ -184,6 +188,8 @@ class DuettEncodeFn(torch.autograd.Function):
             dx_t = encoder_bwd(ct, dx2, pt, _enc_sinks(sinks, f"time_transformers.{l}"), heads, cfgd)   # [B*T1, Ep]
             if dte is not None:
                 ops.axpy(dx_t, dte, 1.0, accumulate=True)
+            if GRAD_READY_HOOK is not None:
+                GRAD_READY_HOOK(f"time_transformers.{l}")
             # time-major grad -> event-major grad of the event encoder's un-normalised output (+ its final norm)
             gname = f"event_transformers.{l}.g_final"
             dx2e = ops.relayout_bwd(dx_t.view(B, T1, V1, cfgd), B, V1, T1, cfgd, src=ce.x2 if fn else None,
@@ -193,6 +199,8 @@ class DuettEncodeFn(torch.autograd.Function):
             dx_e = encoder_bwd(ce, dx2e, pe, _enc_sinks(sinks, f"event_transformers.{l}"), heads, cfgd)  # [B*V1, E]
             if "full_event_embedding.weight" in sinks:
                 ops.colsum(dx_e.view(B, V1 * E), sinks["full_event_embedding.weight"].view(-1), accumulate=True)
+            if GRAD_READY_HOOK is not None:
+                GRAD_READY_HOOK(f"event_transformers.{l}")
             if l > 0:
                 pce, pct = encs[l - 1]
                 gname = f"time_transformers.{l - 1}.g_final"

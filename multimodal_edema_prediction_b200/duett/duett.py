@@ -141,14 +141,14 @@ class _Metric:
         self.kind, self.p, self.y = kind, [], []
 
     def update(self, preds, target):
-        self.p.append(preds.detach().float().cpu()); self.y.append(target.detach().cpu())
+        self.p.append(preds.detach().float()); self.y.append(target.detach())     # stays on the device: no per-step sync
 
     def reset(self):
         self.p, self.y = [], []
 
     def compute(self):
         from sklearn.metrics import average_precision_score, roc_auc_score
-        p, y = torch.cat(self.p).numpy(), torch.cat(self.y).numpy()
+        p, y = torch.cat(self.p).cpu().numpy(), torch.cat(self.y).cpu().numpy()
         return torch.tensor(roc_auc_score(y, p) if self.kind == "auroc" else average_precision_score(y, p))
 
 
@@ -329,12 +329,41 @@ class Model(nn.Module):
         n_timesteps = [len(ts) for ts in times]
         pad_to = int(np.max(n_timesteps))
         dev = self.device
-        xs_ts = torch.stack([F.pad(t, (0, 0, 0, pad_to - t.shape[0])) for t in xs_ts]).to(dev, non_blocking=True)
-        xs_times = torch.stack([F.pad(t, (0, pad_to - t.shape[0])) for t in times]).to(dev, non_blocking=True)
-        xs_static = torch.stack(list(xs_static)).to(dev, non_blocking=True)
+        ragged = any(n != pad_to for n in n_timesteps)
+        if ragged:
+            xs_ts = [F.pad(t, (0, 0, 0, pad_to - t.shape[0])) for t in xs_ts]
+            times = [F.pad(t, (0, pad_to - t.shape[0])) for t in times]
+        xs_ts = self._upload(xs_ts, "ts", dev)
+        xs_times = self._upload(times, "times", dev)
+        xs_static = self._upload(list(xs_static), "static", dev)
         if self.training and self.aug_noise > 0 and not self.pretrain:
             xs_static = xs_static + self.aug_noise * torch.randn_like(xs_static)
         return xs_static, xs_ts, xs_times, n_timesteps
+
+    def _upload(self, tensors, slot, dev):
+        """Stack per-sample tensors and move them to the model's device with ONE copy.  Host inputs are stacked into a
+        pinned, double-buffered staging area (so the H2D copy is asynchronous); inputs already on the device are stacked
+        there (engine._move_lists moves them sample by sample like the reference does)."""
+        t0 = tensors[0]
+        if t0.is_cuda or dev.type != "cuda":
+            return torch.stack(tensors).to(dev, non_blocking=True)
+        shape = (len(tensors),) + tuple(t0.shape)
+        st = self.__dict__.setdefault("_staging", {})
+        key = (slot, shape, t0.dtype)
+        if key not in st:
+            st[key] = {"bufs": [torch.empty(shape, dtype=t0.dtype, pin_memory=True) for _ in range(2)],
+                       "evts": [None, None], "i": 0}
+        s = st[key]
+        i = s["i"]
+        s["i"] = 1 - i
+        if s["evts"][i] is not None:
+            s["evts"][i].synchronize()          # the copy that last used this buffer has completed
+        torch.stack(tensors, out=s["bufs"][i])
+        out = s["bufs"][i].to(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        s["evts"][i] = ev
+        return out
 
     def pretrain_prep_batch(self, x, batch_size):
         """SSL masking with the host numpy RNG, byte-identical to duett/duett.py:189-237 (same draw order: per sample one

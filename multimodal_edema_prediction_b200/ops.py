@@ -40,10 +40,29 @@ def _chk(t, dtype=None, contiguous=True):
     return t
 
 
+PROFILE = None   # bench.py sets this to a list: every GEMM launch then records (tag, flops, bytes, start_evt, end_evt)
+
+
 def gemm_(a, b, **kw):
     global _launches
     _launches += 1
+    if PROFILE is None:
+        return gemm(a, b, **kw)
+    a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N = b.shape[1] if b_mn else b.shape[0]
+    tc = a.dtype == torch.bfloat16 and not kw.get("force_simt", False)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     gemm(a, b, **kw)
+    e1.record()
+    esz = a.element_size()
+    nbytes = (M * K + N * K) * esz
+    for k in ("out", "out2", "res", "aux", "cx"):
+        t = kw.get(k)
+        if t is not None:
+            nbytes += t.numel() * t.element_size() * (2 if (k == "out" and kw.get("accumulate")) else 1)
+    PROFILE.append((("tc" if tc else "ffma"), f"{M}x{N}x{K}{'a' if a_mn else ''}{'b' if b_mn else ''}", 2.0 * M * N * K, nbytes, e0, e1))
 
 
 # ---- relayout / norms -------------------------------------------------------------------------------------------------
