@@ -74,7 +74,11 @@ typedef struct dx_gemm_desc {
   float* row_sumsq;                  /* [M] atomically accumulated */
   float* row_dot;                    /* [M] atomically accumulated (DX_ACT_GELU_BWD) */
   int32_t force_simt;                /* test hook: run the FFMA kernel even for bf16 inputs */
-  int32_t reserved;
+  int32_t batch;                     /* grouped mode: number of independent GEMMs of identical shape (0/1 = single) */
+  /* element strides between consecutive batches (grouped mode; the per-variable embedding MLPs of duett/duett.py:84-86) */
+  int64_t a_bs, b_bs, out_bs, out2_bs, res_bs, aux_bs, cx_bs;
+  int32_t bias_bs;                   /* stride of bias / aux_bias between batches */
+  int32_t rowvec_bs;                 /* stride of the [M] row vectors (row_scale, coef_num, row_sumsq, ...) between batches */
 } dx_gemm_desc;
 
 int dx_gemm(const dx_gemm_desc* d, void* stream);

@@ -75,7 +75,9 @@ class GemmDesc(C.Structure):
         ("cx", C.c_void_p), ("ldc", C.c_int64),
         ("coef_num", C.c_void_p), ("coef_den", C.c_void_p),
         ("row_sumsq", C.c_void_p), ("row_dot", C.c_void_p),
-        ("force_simt", C.c_int32), ("reserved", C.c_int32),
+        ("force_simt", C.c_int32), ("batch", C.c_int32),
+        ("a_bs", C.c_int64), ("b_bs", C.c_int64), ("out_bs", C.c_int64), ("out2_bs", C.c_int64), ("res_bs", C.c_int64),
+        ("aux_bs", C.c_int64), ("cx_bs", C.c_int64), ("bias_bs", C.c_int32), ("rowvec_bs", C.c_int32),
     ]
 
 
@@ -91,17 +93,20 @@ def _declare(L: C.CDLL) -> None:
 
 
 def _ld(t: torch.Tensor) -> int:
-    assert t.dim() == 2 and t.stride(1) == 1, f"need row-major 2-D view, got strides {t.stride()}"
-    return t.stride(0)
+    assert t.dim() in (2, 3) and t.stride(-1) == 1, f"need row-major 2-D (or batched 3-D) view, got strides {t.stride()}"
+    return t.stride(-2)
 
 
 def make_gemm_desc(a: torch.Tensor, b: torch.Tensor, *, a_mn=False, b_mn=False, out=None, out2=None,
                    accumulate=False, act=ACT_NONE, act_dtype=None, row_scale=None, row_scale2=None, bias=None,
                    res=None, aux=None, aux_bias=None, cx=None, coef_num=None, coef_den=None, row_sumsq=None,
                    row_dot=None, force_simt=False) -> GemmDesc:
-    """a: [M,K] (or [K,M] when a_mn), b: [N,K] (or [K,N] when b_mn); both 2-D with unit inner stride."""
-    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
-    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    """a: [M,K] (or [K,M] when a_mn), b: [N,K] (or [K,N] when b_mn); both 2-D with unit inner stride.
+    Grouped mode: every matrix argument carries a leading batch dim ([G,M,K], [G,N,K], out [G,M,N], ...; arbitrary batch
+    stride), bias is [G,N] and row vectors are [G,M]."""
+    batch = a.shape[0] if a.dim() == 3 else 1
+    M, K = (a.shape[-1], a.shape[-2]) if a_mn else (a.shape[-2], a.shape[-1])
+    N, Kb = (b.shape[-1], b.shape[-2]) if b_mn else (b.shape[-2], b.shape[-1])
     if K != Kb:
         raise DxError(f"dx_gemm: contraction mismatch {K} vs {Kb}")
     if a.dtype != b.dtype:
@@ -112,31 +117,39 @@ def make_gemm_desc(a: torch.Tensor, b: torch.Tensor, *, a_mn=False, b_mn=False, 
     d.a_mn, d.b_mn = int(a_mn), int(b_mn)
     d.A, d.lda = a.data_ptr(), _ld(a)
     d.B, d.ldb = b.data_ptr(), _ld(b)
+    d.batch = batch
+    if batch > 1:
+        assert b.dim() == 3 and b.shape[0] == batch
+        d.a_bs, d.b_bs = a.stride(0), b.stride(0)
+        d.bias_bs, d.rowvec_bs = N, M
     if out is not None:
-        assert out.shape == (M, N), (out.shape, M, N)
+        assert tuple(out.shape[-2:]) == (M, N), (out.shape, M, N)
         d.out, d.ldo, d.out_dtype = out.data_ptr(), _ld(out), dtype_code(out.dtype)
+        if batch > 1:
+            d.out_bs = out.stride(0)
     d.accumulate = int(accumulate)
     ad = act_dtype
     for t in (out2, res, aux, cx):
         if t is not None:
-            assert t.shape == (M, N), (t.shape, M, N)
+            assert tuple(t.shape[-2:]) == (M, N), (t.shape, M, N)
             ad = t.dtype if ad is None else ad
             assert t.dtype == ad, "out2/res/aux/cx must share the activation dtype"
     d.act = act
     d.act_dtype = dtype_code(ad if ad is not None else a.dtype)
+    bs = (lambda t: t.stride(0)) if batch > 1 else (lambda t: 0)
     if out2 is not None:
-        d.out2, d.ldo2 = out2.data_ptr(), _ld(out2)
+        d.out2, d.ldo2, d.out2_bs = out2.data_ptr(), _ld(out2), bs(out2)
     if res is not None:
-        d.res, d.ldr = res.data_ptr(), _ld(res)
+        d.res, d.ldr, d.res_bs = res.data_ptr(), _ld(res), bs(res)
     if aux is not None:
-        d.aux, d.ldx = aux.data_ptr(), _ld(aux)
+        d.aux, d.ldx, d.aux_bs = aux.data_ptr(), _ld(aux), bs(aux)
     if cx is not None:
-        d.cx, d.ldc = cx.data_ptr(), _ld(cx)
+        d.cx, d.ldc, d.cx_bs = cx.data_ptr(), _ld(cx), bs(cx)
     for name, t, n in (("row_scale", row_scale, M), ("row_scale2", row_scale2, M), ("bias", bias, N),
                        ("aux_bias", aux_bias, N), ("coef_num", coef_num, M), ("coef_den", coef_den, M),
                        ("row_sumsq", row_sumsq, M), ("row_dot", row_dot, M)):
         if t is not None:
-            assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n, (name, t.shape, t.dtype, n)
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n * batch, (name, t.shape, t.dtype, n)
             setattr(d, name, t.data_ptr())
     d.force_simt = int(force_simt)
     return d

@@ -1,5 +1,9 @@
 // Fused GEMM epilogue shared by the tcgen05 kernel (dx_gemm_tc.cu) and the FFMA kernel (dx_gemm_simt.cu).
-// A caller owns a row `m` and CW consecutive accumulator columns starting at n0.
+// A caller owns a row `m` and CW consecutive accumulator columns starting at n0.  The arithmetic lives in
+// dx_epilogue_math (registers only); the two front-ends differ in how the [M,N] side tensors reach registers:
+//   dx_epilogue_chunk        : direct global loads/stores (thread-per-row vectors; FFMA kernel, unaligned fallbacks)
+//   tcgen05 staged epilogue  : warp-staged through swizzled shared memory so every global access is a full 128 B row
+//                              segment (dx_gemm_tc.cu)
 #pragma once
 #include "dx_common.cuh"
 #include "../../include/duett_b200.h"
@@ -15,6 +19,8 @@ struct DxEpi {
   const void* cx; long long ldc; const float* coef_num; const float* coef_den;
   float* row_sumsq; float* row_dot;
   int vec_ok;  // all leading dims and base pointers allow 16 B vector access at 8-column granularity
+  // batched mode (blockIdx.z = batch index): element offsets added per batch
+  long long out_bs, out2_bs, res_bs, aux_bs, cx_bs; int bias_bs; int rowvec_bs;
 };
 
 static inline DxEpi dx_make_epi(const dx_gemm_desc* d) {
@@ -28,15 +34,37 @@ static inline DxEpi dx_make_epi(const dx_gemm_desc* d) {
   e.aux = d->aux; e.ldx = d->ldx; e.aux_bias = d->aux_bias;
   e.cx = d->cx; e.ldc = d->ldc; e.coef_num = d->coef_num; e.coef_den = d->coef_den;
   e.row_sumsq = d->row_sumsq; e.row_dot = d->row_dot;
-  auto ok = [](const void* p, long long ld, int dtype) {
+  auto ok = [](const void* p, long long ld, long long bs, int dtype) {
     if (!p) return true;
     const long long esz = dtype == DX_BF16 ? 2 : 4;
-    return ((uintptr_t)p % 16 == 0) && ((ld * esz) % 16 == 0);
+    return ((uintptr_t)p % 16 == 0) && ((ld * esz) % 16 == 0) && ((bs * esz) % 16 == 0);
   };
-  e.vec_ok = ok(d->out, d->ldo, d->out_dtype) && ok(d->out2, d->ldo2, d->act_dtype) &&
-             ok(d->res, d->ldr, d->act_dtype) && ok(d->aux, d->ldx, d->act_dtype) &&
-             ok(d->cx, d->ldc, d->act_dtype);
+  e.out_bs = d->out_bs; e.out2_bs = d->out2_bs; e.res_bs = d->res_bs; e.aux_bs = d->aux_bs; e.cx_bs = d->cx_bs;
+  e.bias_bs = d->bias_bs; e.rowvec_bs = d->rowvec_bs;
+  e.vec_ok = ok(d->out, d->ldo, d->out_bs, d->out_dtype) && ok(d->out2, d->ldo2, d->out2_bs, d->act_dtype) &&
+             ok(d->res, d->ldr, d->res_bs, d->act_dtype) && ok(d->aux, d->ldx, d->aux_bs, d->act_dtype) &&
+             ok(d->cx, d->ldc, d->cx_bs, d->act_dtype);
   return e;
+}
+
+// Shift every pointer of the epilogue to batch z (called once per CTA).
+__device__ __forceinline__ void dx_epi_select_batch(DxEpi& e, int z) {
+  if (z == 0) return;
+  const long long osz = e.out_dtype == DX_BF16 ? 2 : 4, asz = e.act_dtype == DX_BF16 ? 2 : 4;
+  if (e.out) e.out = (char*)e.out + z * e.out_bs * osz;
+  if (e.out2) e.out2 = (char*)e.out2 + z * e.out2_bs * asz;
+  if (e.res) e.res = (const char*)e.res + z * e.res_bs * asz;
+  if (e.aux) e.aux = (const char*)e.aux + z * e.aux_bs * asz;
+  if (e.cx) e.cx = (const char*)e.cx + z * e.cx_bs * asz;
+  if (e.bias) e.bias += (long long)z * e.bias_bs;
+  if (e.aux_bias) e.aux_bias += (long long)z * e.bias_bs;
+  const long long rv = (long long)z * e.rowvec_bs;
+  if (e.row_scale) e.row_scale += rv;
+  if (e.row_scale2) e.row_scale2 += rv;
+  if (e.coef_num) e.coef_num += rv;
+  if (e.coef_den) e.coef_den += rv;
+  if (e.row_sumsq) e.row_sumsq += rv;
+  if (e.row_dot) e.row_dot += rv;
 }
 
 // Load CW (multiple of 8) values of a [.., ld] matrix row as float.
@@ -110,14 +138,13 @@ __device__ __forceinline__ void dx_epi_store(void* base, long long ld, int dtype
   }
 }
 
-// Applies the epilogue to CW accumulator columns of row m (m < M guaranteed by the caller).
-// rs_acc / rd_acc collect the row reductions; the caller flushes them with one atomicAdd per row.
+// Register-only arithmetic of the epilogue.  v: accumulator columns (in) -> final `out` values (out).
+// r / a / c: preloaded residual, aux and cx values (ignored when the corresponding pointer in `e` is null).
+// o2: receives the `out2` values when has_out2() (pre-activation for GELU, unscaled dpre for GELU_BWD).
 template <int CW>
-__device__ __forceinline__ void dx_epilogue_chunk(const DxEpi& e, int m, int n0, float (&v)[CW], float& rs_acc,
-                                                  float& rd_acc) {
-  const int nvalid = min(CW, e.N - n0);
-  if (nvalid <= 0) return;
-  const bool vec = e.vec_ok != 0;
+__device__ __forceinline__ void dx_epilogue_math(const DxEpi& e, int m, int n0, int nvalid, float (&v)[CW],
+                                                 const float (&r)[CW], const float (&a)[CW], const float (&c)[CW],
+                                                 float (&o2)[CW], float& rs_acc, float& rd_acc) {
   if (e.row_scale) {
     const float s = e.row_scale[m];
 #pragma unroll
@@ -128,50 +155,41 @@ __device__ __forceinline__ void dx_epilogue_chunk(const DxEpi& e, int m, int n0,
     for (int i = 0; i < CW; ++i) v[i] += (i < nvalid) ? __ldg(e.bias + n0 + i) : 0.f;
   }
   if (e.act == DX_ACT_GELU) {
-    if (e.out2) dx_epi_store<CW>(e.out2, e.ldo2, e.act_dtype, 0, m, n0, nvalid, vec, v);
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = dx_gelu(v[i]);
+    for (int i = 0; i < CW; ++i) { o2[i] = v[i]; v[i] = dx_gelu(v[i]); }
   } else if (e.act == DX_ACT_RELU) {
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
   } else if (e.act == DX_ACT_TANH) {
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = tanhf(v[i]);
-  } else if (e.act >= DX_ACT_GELU_BWD) {
-    float a[CW];
-    dx_epi_load<CW>(e.aux, e.ldx, e.act_dtype, m, n0, nvalid, vec, a);
-    if (e.act == DX_ACT_GELU_BWD) {
-      float rd = 0.f;
+  } else if (e.act == DX_ACT_GELU_BWD) {
+    float rd = 0.f;
 #pragma unroll
-      for (int i = 0; i < CW; ++i) {
-        v[i] *= dx_gelu_grad(a[i]);
-        const float ab = (e.aux_bias && i < nvalid) ? __ldg(e.aux_bias + n0 + i) : 0.f;
-        rd += (i < nvalid) ? v[i] * (a[i] - ab) : 0.f;
-      }
-      rd_acc += rd;
-      if (e.out2) dx_epi_store<CW>(e.out2, e.ldo2, e.act_dtype, 0, m, n0, nvalid, vec, v);
-      if (e.row_scale2) {
-        const float s2 = e.row_scale2[m];
-#pragma unroll
-        for (int i = 0; i < CW; ++i) v[i] *= s2;
-      }
-    } else if (e.act == DX_ACT_RELU_BWD) {
-#pragma unroll
-      for (int i = 0; i < CW; ++i) v[i] = a[i] > 0.f ? v[i] : 0.f;
-    } else {  // TANH_BWD
-#pragma unroll
-      for (int i = 0; i < CW; ++i) v[i] *= (1.f - a[i] * a[i]);
+    for (int i = 0; i < CW; ++i) {
+      v[i] *= dx_gelu_grad(a[i]);
+      const float ab = (e.aux_bias && i < nvalid) ? __ldg(e.aux_bias + n0 + i) : 0.f;
+      rd += (i < nvalid) ? v[i] * (a[i] - ab) : 0.f;
+      o2[i] = v[i];
     }
+    rd_acc += rd;
+    if (e.row_scale2) {
+      const float s2 = e.row_scale2[m];
+#pragma unroll
+      for (int i = 0; i < CW; ++i) v[i] *= s2;
+    }
+  } else if (e.act == DX_ACT_RELU_BWD) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = a[i] > 0.f ? v[i] : 0.f;
+  } else if (e.act == DX_ACT_TANH_BWD) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] *= (1.f - a[i] * a[i]);
   }
   if (e.res) {
-    float r[CW];
-    dx_epi_load<CW>(e.res, e.ldr, e.act_dtype, m, n0, nvalid, vec, r);
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] += r[i];
   }
   if (e.cx) {
-    float c[CW];
-    dx_epi_load<CW>(e.cx, e.ldc, e.act_dtype, m, n0, nvalid, vec, c);
     const float coef = e.coef_num[m] / fmaxf(e.coef_den[m], 1e-24f);
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] -= c[i] * coef;
@@ -182,7 +200,38 @@ __device__ __forceinline__ void dx_epilogue_chunk(const DxEpi& e, int m, int n0,
     for (int i = 0; i < CW; ++i) s += (i < nvalid) ? v[i] * v[i] : 0.f;
     rs_acc += s;
   }
-  if (e.out) dx_epi_store<CW>(e.out, e.ldo, e.out_dtype, e.accumulate, m, n0, nvalid, vec, v);
+}
+
+__device__ __forceinline__ bool dx_epi_has_out2(const DxEpi& e) {
+  return e.out2 != nullptr && (e.act == DX_ACT_GELU || e.act == DX_ACT_GELU_BWD);
+}
+
+// Direct-global front-end: applies the epilogue to CW accumulator columns of row m (m < M guaranteed by the caller),
+// 8 columns (one 16 B bf16 vector) at a time to keep the live register set small.
+// rs_acc / rd_acc collect the row reductions; the caller flushes them with one atomicAdd per row.
+__device__ __forceinline__ void dx_epilogue_piece(const DxEpi& e, int m, int n0, float (&v)[8], float& rs_acc, float& rd_acc) {
+  const int nvalid = min(8, e.N - n0);
+  if (nvalid <= 0) return;
+  const bool vec = e.vec_ok != 0;
+  float r[8], a[8], c[8], o2[8];
+  if (e.res) dx_epi_load<8>(e.res, e.ldr, e.act_dtype, m, n0, nvalid, vec, r);
+  if (e.aux) dx_epi_load<8>(e.aux, e.ldx, e.act_dtype, m, n0, nvalid, vec, a);
+  if (e.cx) dx_epi_load<8>(e.cx, e.ldc, e.act_dtype, m, n0, nvalid, vec, c);
+  dx_epilogue_math<8>(e, m, n0, nvalid, v, r, a, c, o2, rs_acc, rd_acc);
+  if (dx_epi_has_out2(e)) dx_epi_store<8>(e.out2, e.ldo2, e.act_dtype, 0, m, n0, nvalid, vec, o2);
+  if (e.out) dx_epi_store<8>(e.out, e.ldo, e.out_dtype, e.accumulate, m, n0, nvalid, vec, v);
+}
+
+template <int CW>
+__device__ __forceinline__ void dx_epilogue_chunk(const DxEpi& e, int m, int n0, float (&v)[CW], float& rs_acc,
+                                                  float& rd_acc) {
+#pragma unroll
+  for (int i = 0; i < CW; i += 8) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = v[i + j];
+    dx_epilogue_piece(e, m, n0 + i, t, rs_acc, rd_acc);
+  }
 }
 
 __device__ __forceinline__ void dx_epilogue_flush_row(const DxEpi& e, int m, float rs_acc, float rd_acc) {

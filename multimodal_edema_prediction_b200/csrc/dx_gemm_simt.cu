@@ -10,7 +10,10 @@ constexpr int BM = 64, BN = 128, BK = 16, NT = 256;
 template <typename TI>
 __global__ void __launch_bounds__(NT) dx_gemm_simt_kernel(const TI* __restrict__ A, long long sam, long long sak,
                                                          const TI* __restrict__ B, long long sbn, long long sbk,
-                                                         int K, DxEpi e) {
+                                                         int K, DxEpi e, long long a_bs, long long b_bs) {
+  A += (long long)blockIdx.z * a_bs;
+  B += (long long)blockIdx.z * b_bs;
+  dx_epi_select_batch(e, blockIdx.z);
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int t = threadIdx.x;
@@ -76,13 +79,13 @@ int dx_gemm_simt_launch(const dx_gemm_desc* d, cudaStream_t stream) {
   DxEpi e = dx_make_epi(d);
   const long long sam = d->a_mn ? 1 : d->lda, sak = d->a_mn ? d->lda : 1;
   const long long sbn = d->b_mn ? 1 : d->ldb, sbk = d->b_mn ? d->ldb : 1;
-  dim3 grid(dx_ceil_div(d->N, BN), dx_ceil_div(d->M, BM));
+  dim3 grid(dx_ceil_div(d->N, BN), dx_ceil_div(d->M, BM), d->batch > 1 ? d->batch : 1);
   if (d->in_dtype == DX_F32) {
     dx_gemm_simt_kernel<float><<<grid, NT, 0, stream>>>((const float*)d->A, sam, sak, (const float*)d->B, sbn, sbk,
-                                                        d->K, e);
+                                                        d->K, e, d->a_bs, d->b_bs);
   } else {
     dx_gemm_simt_kernel<bf16><<<grid, NT, 0, stream>>>((const bf16*)d->A, sam, sak, (const bf16*)d->B, sbn, sbk,
-                                                       d->K, e);
+                                                       d->K, e, d->a_bs, d->b_bs);
   }
   DX_LAUNCH_CHECK();
   return DX_OK;

@@ -2,12 +2,19 @@
 // tcgen05.mma kind::f16 (one elected thread) -> fp32 accumulator in TMEM -> tcgen05.ld epilogue.
 //
 //   acc[m,n] = sum_k A(m,k) * B(n,k); A and B each K-major or MN-major (so X@W^T, dY@W and dY^T@X all run
-//   from the tensors as they sit in HBM, without transposed copies).
+//   from the tensors as they sit in HBM, without transposed copies).  Grouped mode: blockIdx.z selects one of
+//   `batch` independent problems through the third dimension of the tensor maps.
 //
 // CTA = 128 x BN output tile, BLOCK_K = 64 (one 128 B swizzle row of bf16), STAGES-deep mbarrier ring.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (TMEM lane quadrant = warp % 4).
-// Large-K shapes use BN=256 / 4 stages (1 CTA per SM, 96 B/clk smem operand traffic per MMA);
-// small-K, HBM-bound shapes use BN=128 / 2-3 stages so that 2-3 CTAs share an SM and epilogues overlap mainloops.
+// Large-K shapes use BN=256 (1 CTA per SM, 96 B/clk smem operand traffic per MMA); small-K, HBM-bound shapes use
+// BN=128 with 2 stages so that 2 CTAs share an SM and epilogues overlap mainloops.
+//
+// Epilogue front-ends:
+//   STAGED  (bf16 side tensors, 16 B aligned): each epilogue warp moves 32 rows x 64 columns at a time through its own
+//           XOR-swizzled shared-memory staging blocks — global loads of res/cx/aux and stores of out/out2 are full
+//           128 B row segments (4 rows per warp instruction), the thread-per-row TMEM layout only ever touches smem.
+//   direct  : thread-per-row 16 B vectors straight to global (fp32 outputs such as dW accumulation, unaligned shapes).
 #include "dx_gemm_epilogue.cuh"
 #include <cudaTypedefs.h>
 
@@ -16,6 +23,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int NTHREADS = 192;
+constexpr int STG_BYTES = 32 * 128;   // one staging block: 32 rows x 64 bf16
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -26,7 +34,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -46,15 +53,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {
-      printf("dx_gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      printf("dx_gemm_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
       __trap();
     }
   }
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -116,10 +124,50 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 struct TcParams {
   int K;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // descriptor byte offsets (test-overridable)
+  int stage_bufs;                        // staging blocks per epilogue warp (STAGED only): 1..3
 };
 
+// ---- warp-staged tile movement (STAGED epilogue) -----------------------------------------------------------
+// A staging block holds 32 rows x 8 pieces of 16 B; piece p of row r lives at r*128 + ((p ^ (r & 7)) << 4), which is
+// conflict-free both for the row-per-lane view (epilogue math) and for the 8-lanes-per-row view (global traffic).
+__device__ __forceinline__ uint32_t stg_off(int r, int p) { return (uint32_t)(r * 128 + ((p ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ void stage_load(uint8_t* buf, const void* base, long long ld, int m_base, int n0, int M, int N,
+                                           int lane) {
+  const int piece = lane & 7, rsub = lane >> 3;
+  const int col = n0 + piece * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    const int gm = m_base + r;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (gm < M && col < N) val = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + (long long)gm * ld + col));
+    *reinterpret_cast<uint4*>(buf + stg_off(r, piece)) = val;
+  }
+}
+__device__ __forceinline__ void stage_store(const uint8_t* buf, void* base, long long ld, int m_base, int n0, int M, int N,
+                                            int lane) {
+  const int piece = lane & 7, rsub = lane >> 3;
+  const int col = n0 + piece * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    const int gm = m_base + r;
+    if (gm < M && col < N)
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + (long long)gm * ld + col) =
+          *reinterpret_cast<const uint4*>(buf + stg_off(r, piece));
+  }
+}
+// this lane's row, one 16 B piece (8 consecutive bf16 columns) as floats / from floats
+__device__ __forceinline__ void stage_piece_get(const uint8_t* buf, int lane, int piece, float (&v)[8]) {
+  dx_ld8(reinterpret_cast<const bf16*>(buf + stg_off(lane, piece)), v);
+}
+__device__ __forceinline__ void stage_piece_put(uint8_t* buf, int lane, int piece, const float (&v)[8]) {
+  dx_st8(reinterpret_cast<bf16*>(buf + stg_off(lane, piece)), v);
+}
+
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED>
 __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, TcParams p,
                                                              DxEpi e) {
@@ -133,9 +181,10 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, z = blockIdx.z;
   const int num_kb = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -169,16 +218,16 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
         mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
         const int k0 = kb * BK;
         if (!A_MN) {
-          tma_load_2d(sa, &tmA, full_bar + s, k0, m0);  // box {64 k, 128 m}
+          tma_load_3d(sa, &tmA, full_bar + s, k0, m0, z);  // box {64 k, 128 m, 1}
         } else {
 #pragma unroll
-          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, full_bar + s, m0 + c * 64, k0);  // {64 m, 64 k}
+          for (int c = 0; c < BM / 64; ++c) tma_load_3d(sa + c * 8192, &tmA, full_bar + s, m0 + c * 64, k0, z);  // {64 m, 64 k, 1}
         }
         if (!B_MN) {
-          tma_load_2d(sb, &tmB, full_bar + s, k0, n0);  // box {64 k, BN n}
+          tma_load_3d(sb, &tmB, full_bar + s, k0, n0, z);  // box {64 k, BN n, 1}
         } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, full_bar + s, n0 + c * 64, k0);
+          for (int c = 0; c < BN / 64; ++c) tma_load_3d(sb + c * 8192, &tmB, full_bar + s, n0 + c * 64, k0, z);
         }
       }
     }
@@ -211,18 +260,72 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     __syncwarp();
   } else {
     // ===== epilogue: warp w reads TMEM lanes [32*(w%4), +32) =====
+    dx_epi_select_batch(e, z);
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    const int m_base = m0 + q * 32;
+    const int m = m_base + lane;
+    const bool row_ok = m < e.M;
     float rs = 0.f, rd = 0.f;
+    if (!STAGED) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);  // warp-collective
-      if (m < e.M) dx_epilogue_chunk<32>(e, m, n0 + c * 32, v, rs, rd);
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);  // warp-collective
+        if (row_ok) dx_epilogue_chunk<32>(e, m, n0 + c * 32, v, rs, rd);
+      }
+    } else {
+      uint8_t* bufR = stg_base + (warp - 2) * p.stage_bufs * STG_BYTES;  // out (and res, in place)
+      uint8_t* bufX = bufR + STG_BYTES;                                    // aux or cx
+      uint8_t* bufO = bufR + (p.stage_bufs - 1) * STG_BYTES;               // out2 (last block)
+      const bool has_o2 = dx_epi_has_out2(e);
+      const void* xsrc = e.aux ? e.aux : e.cx;
+      const long long xld = e.aux ? e.ldx : e.ldc;
+      bool waited = false;
+#pragma unroll 1
+      for (int sc = 0; sc < BN / 64; ++sc) {
+        const int nc = n0 + sc * 64;
+        if (nc >= e.N) break;
+        // side tensors do not depend on the accumulator: fetch them while the mainloop is still running
+        if (e.res) stage_load(bufR, e.res, e.ldr, m_base, nc, e.M, e.N, lane);
+        if (xsrc) stage_load(bufX, xsrc, xld, m_base, nc, e.M, e.N, lane);
+        __syncwarp();
+        if (!waited) {
+          mbar_wait(tmem_full_bar, 0);
+          tc_fence_after();
+          waited = true;
+        }
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * 64 + half * 32), v);  // warp-collective
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int piece = half * 4 + j;
+            const int ncol = nc + piece * 8;
+            float t[8], r[8], a[8], o2[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
+            if (e.res) stage_piece_get(bufR, lane, piece, r);
+            if (xsrc) stage_piece_get(bufX, lane, piece, a);
+            // aux and cx are mutually exclusive in every staged launch: `a` serves as both. N % 8 == 0 -> whole pieces.
+            if (row_ok && ncol < e.N) dx_epilogue_math<8>(e, m, ncol, 8, t, r, a, a, o2, rs, rd);
+            stage_piece_put(bufR, lane, piece, t);
+            if (has_o2) stage_piece_put(bufO, lane, piece, o2);
+          }
+        }
+        __syncwarp();
+        if (e.out) stage_store(bufR, e.out, e.ldo, m_base, nc, e.M, e.N, lane);
+        if (has_o2) stage_store(bufO, e.out2, e.ldo2, m_base, nc, e.M, e.N, lane);
+        __syncwarp();
+      }
+      if (!waited) {  // tile entirely right of N (cannot happen with the host grid, kept for safety)
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+      }
     }
-    if (m < e.M) dx_epilogue_flush_row(e, m, rs, rd);
+    if (row_ok) dx_epilogue_flush_row(e, m, rs, rd);
   }
   tc_fence_before();
   __syncthreads();
@@ -247,49 +350,62 @@ int get_encode_fn() {
   return DX_OK;
 }
 
-// 2-D bf16 tensor map: dim0 = contiguous (size inner), dim1 = rows (size outer, stride ld elements).
-int make_tmap(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int box_inner,
-              int box_outer) {
-  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+// 3-D bf16 tensor map: dim0 = contiguous (size inner), dim1 = rows (size outer, stride ld elements),
+// dim2 = batch (stride bs elements).
+int make_tmap(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int batch, long long bs,
+              int box_inner, int box_outer) {
+  cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(batch > 1 ? batch : 1)};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? bs * 2 : ld * 2)};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    dx_set_error("cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld ld=%lld box=%dx%d base=%p", (int)r, inner,
-                 outer, ld, box_inner, box_outer, base);
+    dx_set_error("cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld ld=%lld batch=%d bs=%lld box=%dx%d base=%p",
+                 (int)r, inner, outer, ld, batch, bs, box_inner, box_outer, base);
     return DX_ERR_CUDA;
   }
   return DX_OK;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED>
 int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, const DxEpi& e,
                cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
-  auto kern = dx_gemm_tc_kernel<BN, STAGES, A_MN, B_MN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
+  const int smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/ +
+                   (STAGED ? 4 * p.stage_bufs * STG_BYTES : 0);
+  auto kern = dx_gemm_tc_kernel<BN, STAGES, A_MN, B_MN, STAGED>;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
   }
-  dim3 grid(dx_ceil_div(d->N, BN), dx_ceil_div(d->M, BM));
-  kern<<<grid, NTHREADS, SMEM, stream>>>(ta, tb, p, e);
+  dim3 grid(dx_ceil_div(d->N, BN), dx_ceil_div(d->M, BM), d->batch > 1 ? d->batch : 1);
+  kern<<<grid, NTHREADS, smem, stream>>>(ta, tb, p, e);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool STAGED>
 int launch_major(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& ta, const CUtensorMap& tb,
                  const TcParams& p, const DxEpi& e, cudaStream_t stream) {
-  if (bn == 256 && stages == 4) return launch_cfg<256, 4, A_MN, B_MN>(d, ta, tb, p, e, stream);
-  if (bn == 128 && stages == 3) return launch_cfg<128, 3, A_MN, B_MN>(d, ta, tb, p, e, stream);
-  if (bn == 128 && stages == 6) return launch_cfg<128, 6, A_MN, B_MN>(d, ta, tb, p, e, stream);
-  if (bn == 64 && stages == 4) return launch_cfg<64, 4, A_MN, B_MN>(d, ta, tb, p, e, stream);
+  if (bn == 256 && stages == 4) return launch_cfg<256, 4, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
+  if (bn == 256 && stages == 3) return launch_cfg<256, 3, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
+  if (bn == 128 && stages == 2) return launch_cfg<128, 2, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
+  if (bn == 128 && stages == 3) return launch_cfg<128, 3, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
+  if (bn == 128 && stages == 6) return launch_cfg<128, 6, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
+  if (bn == 64 && stages == 4) return launch_cfg<64, 4, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
   dx_set_error("dx_gemm_tc: unsupported tile config BN=%d stages=%d", bn, stages);
   return DX_ERR_UNSUPPORTED;
+}
+
+template <bool STAGED>
+int launch_staged(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p,
+                  const DxEpi& e, cudaStream_t stream) {
+  if (!d->a_mn && !d->b_mn) return launch_major<false, false, STAGED>(d, bn, stages, ta, tb, p, e, stream);
+  if (!d->a_mn && d->b_mn) return launch_major<false, true, STAGED>(d, bn, stages, ta, tb, p, e, stream);
+  if (d->a_mn && !d->b_mn) return launch_major<true, false, STAGED>(d, bn, stages, ta, tb, p, e, stream);
+  return launch_major<true, true, STAGED>(d, bn, stages, ta, tb, p, e, stream);
 }
 
 }  // namespace
@@ -298,24 +414,35 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
                       cudaStream_t stream) {
   int rc = get_encode_fn();
   if (rc) return rc;
+  const int batch = d->batch > 1 ? d->batch : 1;
   DX_CHECK_ARG(d->in_dtype == DX_BF16, "dx_gemm_tc: inputs must be bf16");
   DX_CHECK_ARG(((uintptr_t)d->A % 16 == 0) && ((uintptr_t)d->B % 16 == 0), "dx_gemm_tc: A/B must be 16 B aligned");
   DX_CHECK_ARG((d->lda % 8 == 0) && (d->ldb % 8 == 0), "dx_gemm_tc: lda/ldb must be multiples of 8 (got %lld, %lld)",
                (long long)d->lda, (long long)d->ldb);
-  if (bn <= 0) {
-    // Heuristic: deep-K contractions get the 128x256 tile; shallow-K (HBM-bound) ones get 128x128 with
-    // several CTAs per SM; narrow outputs get 128x64.
+  DX_CHECK_ARG(batch == 1 || ((d->a_bs % 8 == 0) && (d->b_bs % 8 == 0)), "dx_gemm_tc: batch strides must be multiples of 8");
+  DX_CHECK_ARG(batch <= 65535, "dx_gemm_tc: batch too large");
+  DxEpi e = dx_make_epi(d);
+  // Staged (coalesced) epilogue whenever every [M,N] side tensor is bf16 and 16 B aligned.
+  const bool has_o2 = d->out2 != nullptr && (d->act == DX_ACT_GELU || d->act == DX_ACT_GELU_BWD);
+  const bool any_side = d->out || d->res || d->aux || d->cx;
+  const bool staged = any_side && e.vec_ok && d->act_dtype == DX_BF16 && (!d->out || d->out_dtype == DX_BF16) &&
+                      !d->accumulate && (d->N % 8 == 0) && !(d->aux && d->cx);
+  const int nbufs = 1 + ((d->aux || d->cx) ? 1 : 0) + (has_o2 ? 1 : 0);
+  const bool user_cfg = bn > 0;
+  if (!user_cfg) {
+    // Heuristic: deep-K contractions get the 128x256 tile; shallow-K (HBM-bound) ones get 128x128 / 2 stages so two
+    // CTAs share an SM; narrow outputs get 128x64.
     if (d->N <= 64) { bn = 64; stages = 4; }
-    else if (d->K >= 1024 && d->N >= 256) { bn = 256; stages = 4; }
+    else if (d->K >= 1024 && d->N >= 256) { bn = 256; stages = (staged && nbufs == 3) ? 3 : 4; }
     else if (d->K >= 1024) { bn = 128; stages = 6; }
-    else { bn = 128; stages = 3; }
+    else { bn = 128; stages = staged ? 2 : 3; }
   }
   CUtensorMap ta, tb;
-  if (!d->a_mn) rc = make_tmap(&ta, d->A, d->K, d->M, d->lda, BK, BM);
-  else rc = make_tmap(&ta, d->A, d->M, d->K, d->lda, 64, BK);
+  if (!d->a_mn) rc = make_tmap(&ta, d->A, d->K, d->M, d->lda, batch, d->a_bs, BK, BM);
+  else rc = make_tmap(&ta, d->A, d->M, d->K, d->lda, batch, d->a_bs, 64, BK);
   if (rc) return rc;
-  if (!d->b_mn) rc = make_tmap(&tb, d->B, d->K, d->N, d->ldb, BK, bn);
-  else rc = make_tmap(&tb, d->B, d->N, d->K, d->ldb, 64, BK);
+  if (!d->b_mn) rc = make_tmap(&tb, d->B, d->K, d->N, d->ldb, batch, d->b_bs, BK, bn);
+  else rc = make_tmap(&tb, d->B, d->N, d->K, d->ldb, batch, d->b_bs, 64, BK);
   if (rc) return rc;
   TcParams p;
   p.K = d->K;
@@ -326,9 +453,7 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
   p.a_sbo = a_sbo >= 0 ? a_sbo : 1024;
   p.b_lbo = b_lbo >= 0 ? b_lbo : (d->b_mn ? 8192 : 16);
   p.b_sbo = b_sbo >= 0 ? b_sbo : 1024;
-  DxEpi e = dx_make_epi(d);
-  if (!d->a_mn && !d->b_mn) return launch_major<false, false>(d, bn, stages, ta, tb, p, e, stream);
-  if (!d->a_mn && d->b_mn) return launch_major<false, true>(d, bn, stages, ta, tb, p, e, stream);
-  if (d->a_mn && !d->b_mn) return launch_major<true, false>(d, bn, stages, ta, tb, p, e, stream);
-  return launch_major<true, true>(d, bn, stages, ta, tb, p, e, stream);
+  p.stage_bufs = nbufs;
+  if (staged) return launch_staged<true>(d, bn, stages, ta, tb, p, e, stream);
+  return launch_staged<false>(d, bn, stages, ta, tb, p, e, stream);
 }
