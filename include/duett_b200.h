@@ -130,21 +130,28 @@ int dx_attn_bwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_
                 int64_t dv_bs, int64_t dv_rs, const float* lse, float* D_ws, int B, int H, int Sq, int Sk, int dh,
                 int dtype, void* stream);
 
-/* Value/count embedding into psi[B,T+1,V+1,d]: count lookup (n_obs_embedding, clip 0..15), V grouped MLPs
+/* Value/count embedding into psi[B,T+1,V+1,d] (duett/duett.py:245-266 == models/main_architecture_duett.py:31-65, the
+ * per-variable Python loop): count lookup (n_obs_embedding, clip 0..15), V grouped MLPs
  * Linear(2,64)-ReLU-BatchNorm(batch stats over B*T)-Linear(64,d), static column, [REP] row, MASK substitution.
- * xs: [B,T,2V+1] f32 (values | counts | masked-step flag).  Stacked parameters: W0 [V,64,2], b0/gamma/beta/run_* [V,64],
- * W4 [V,d,64], b4 [V,d], nobs [16], special [8,d], tab [B,d] (tab_encoder output).  Saves mean/rstd [V,64].
- * Replaces: duett/duett.py:245-266 == models/main_architecture_duett.py:31-65 (the per-variable Python loop). */
-int dx_embed_fwd(const float* xs, int B, int T, int V, int d, const float* W0, const float* b0, const float* gamma,
-                 const float* beta, float* run_mean, float* run_var, const float* W4, const float* b4, const float* nobs,
-                 const float* special, const float* tab, void* psi, int act_dtype, double* stats_ws, float* mean,
-                 float* rstd, int training, void* stream);
-/* Parameter gradients are accumulated (f32); dtab [B,d] is written.  dhn_ws [V,B*T,64] f32, dgb_ws [2,V,64] f32 scratch. */
-int dx_embed_bwd(const float* xs, int B, int T, int V, int d, const float* W0, const float* b0, const float* gamma,
-                 const float* beta, const float* W4, const float* nobs, const float* mean, const float* rstd,
-                 const void* dpsi, int act_dtype, float* dhn_ws, float* dgb_ws, float* dW0, float* db0, float* dgamma,
-                 float* dbeta, float* dW4, float* db4, float* dnobs, float* dspecial, float* dtab, int training,
-                 void* stream);
+ * The 64->d contraction of all variables is ONE grouped dx_gemm (batch = V) writing into the strided psi view; these
+ * entry points are the pieces around it.  xs: [B,T,2V+1] f32 (values | counts | masked-step flag); stacked parameters
+ * W0 [V,64,2], b0/gamma/beta/run_* [V,64], nobs [16], special [8,d], tab [B,d] (tab_encoder output);
+ * hn / dhn: [V, B*(T+1), 64] in the act dtype. */
+int dx_embed_stats(const float* xs, int B, int T, int V, const float* W0, const float* b0, const float* nobs, float* run_mean,
+                   float* run_var, double* stats_ws, float* mean, float* rstd, int training, void* stream);
+int dx_embed_hidden(const float* xs, int B, int T, int V, const float* W0, const float* b0, const float* nobs,
+                    const float* gamma, const float* beta, const float* mean, const float* rstd, void* hn, int act_dtype,
+                    void* stream);
+int dx_embed_special(const float* xs, int B, int T, int V, int d, const float* special, const float* tab, void* psi,
+                     int act_dtype, void* stream);
+/* backward: dspecial accumulated, dtab written, special cells of dpsi zeroed in place */
+int dx_embed_special_bwd(const float* xs, int B, int T, int V, int d, void* dpsi, int act_dtype, float* dspecial, float* dtab,
+                         void* stream);
+int dx_embed_bn_reduce(const float* xs, int B, int T, int V, const float* W0, const float* b0, const float* nobs,
+                       const float* mean, const float* rstd, const void* dhn, int act_dtype, float* dgb, void* stream);
+int dx_embed_bwd_front(const float* xs, int B, int T, int V, const float* W0, const float* b0, const float* nobs,
+                       const float* gamma, const float* mean, const float* rstd, const void* dhn, int act_dtype,
+                       const float* dgb, float* dW0, float* db0, float* dnobs, int training, void* stream);
 
 /* BatchNormLastDim on [R,C] f32 (duett/duett.py:11-22; tab_encoder, cve, head) and LayerNorm on [R,C]
  * (models/main_architecture_duett.py:745-774).  Backward accumulates dw/db; dx may be NULL. */

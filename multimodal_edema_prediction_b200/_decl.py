@@ -16,8 +16,12 @@ SIGNATURES = {
     "dx_attn_bwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, P, I, I, I, I, I, I, P],
     "dx_rowdot_scale": [P, P, P, P, I, I, I, P],
     "dx_scalenorm_scale": [P, P, F, P, I, P],
-    "dx_embed_fwd": [P, I, I, I, I, P, P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, I, P],
-    "dx_embed_bwd": [P, I, I, I, I, P, P, P, P, P, P, P, P, P, I, P, P, P, P, P, P, P, P, P, P, P, I, P],
+    "dx_embed_stats": [P, I, I, I, P, P, P, P, P, P, P, P, I, P],
+    "dx_embed_hidden": [P, I, I, I, P, P, P, P, P, P, P, P, I, P],
+    "dx_embed_special": [P, I, I, I, I, P, P, P, I, P],
+    "dx_embed_special_bwd": [P, I, I, I, I, P, I, P, P, P],
+    "dx_embed_bn_reduce": [P, I, I, I, P, P, P, P, P, P, I, P, P],
+    "dx_embed_bwd_front": [P, I, I, I, P, P, P, P, P, P, P, I, P, P, P, P, I, P],
     "dx_bn2d_fwd": [P, I, I, P, P, P, P, P, P, P, I, P],
     "dx_bn2d_bwd": [P, P, I, I, P, P, P, P, P, P, I, P],
     "dx_layernorm_fwd": [P, I, I, P, P, P, P, P, I, P],

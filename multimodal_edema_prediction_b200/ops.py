@@ -49,20 +49,22 @@ def gemm_(a, b, **kw):
     if PROFILE is None:
         return gemm(a, b, **kw)
     a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
-    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
-    N = b.shape[1] if b_mn else b.shape[0]
+    G = a.shape[0] if a.dim() == 3 else 1
+    M, K = (a.shape[-1], a.shape[-2]) if a_mn else (a.shape[-2], a.shape[-1])
+    N = b.shape[-1] if b_mn else b.shape[-2]
     tc = a.dtype == torch.bfloat16 and not kw.get("force_simt", False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     gemm(a, b, **kw)
     e1.record()
     esz = a.element_size()
-    nbytes = (M * K + N * K) * esz
+    nbytes = G * (M * K + N * K) * esz
     for k in ("out", "out2", "res", "aux", "cx"):
         t = kw.get(k)
         if t is not None:
             nbytes += t.numel() * t.element_size() * (2 if (k == "out" and kw.get("accumulate")) else 1)
-    PROFILE.append((("tc" if tc else "ffma"), f"{M}x{N}x{K}{'a' if a_mn else ''}{'b' if b_mn else ''}", 2.0 * M * N * K, nbytes, e0, e1))
+    PROFILE.append((("tc" if tc else "ffma"), f"{G}*" * (G > 1) + f"{M}x{N}x{K}{'a' if a_mn else ''}{'b' if b_mn else ''}",
+                    2.0 * G * M * N * K, nbytes, e0, e1))
 
 
 # ---- relayout / norms -------------------------------------------------------------------------------------------------
@@ -168,31 +170,59 @@ def attn_bwd(q, k, v, o, go, lse, heads, dq, dk, dv):
 
 
 # ---- embedding ---------------------------------------------------------------------------------------------------------
+def _embed_hidden(xs, V, W0, b0, nobs, gamma, beta, mean, rstd, act_dtype):
+    B, T, _ = xs.shape
+    hn = torch.empty((V, B * (T + 1), 64), device=xs.device, dtype=act_dtype)
+    _call("dx_embed_hidden", _p(xs), B, T, V, _p(W0), _p(b0), _p(nobs), _p(gamma), _p(beta), _p(mean), _p(rstd), _p(hn),
+          L.dtype_code(act_dtype))
+    return hn
+
+
+def _psi_groups(psi, B, T1, V, d):
+    """[V, B*T1, d] strided view of psi[B,T1,V+1,d]: group v = variable v's column (row stride (V+1)*d, group stride d)."""
+    return psi.view(B * T1, V + 1, d)[:, :V, :].permute(1, 0, 2)
+
+
 def embed_fwd(xs, V, d, W0, b0, gamma, beta, run_mean, run_var, W4, b4, nobs, special, tab, act_dtype, training):
+    """psi[B,T+1,V+1,d] = embedding of the binned grid: stats -> hidden -> ONE grouped tensor-core GEMM over the V
+    variables (64 -> d, written into the strided psi view) -> special-cell substitution."""
     B, T, _ = xs.shape
     dev = xs.device
-    psi = torch.empty((B, T + 1, V + 1, d), device=dev, dtype=act_dtype)
+    for t in (xs, W0, b0, gamma, beta, W4, b4, nobs, special, tab):
+        _chk(t, torch.float32)
     stats = torch.empty((V, 64, 2), device=dev, dtype=torch.float64) if training else None
     mean = torch.empty((V, 64), device=dev, dtype=torch.float32)
     rstd = torch.empty((V, 64), device=dev, dtype=torch.float32)
-    for t in (xs, W0, b0, gamma, beta, W4, b4, nobs, special, tab):
-        _chk(t, torch.float32)
-    _call("dx_embed_fwd", _p(xs), B, T, V, d, _p(W0), _p(b0), _p(gamma), _p(beta), _p(run_mean), _p(run_var), _p(W4), _p(b4),
-          _p(nobs), _p(special), _p(tab), _p(psi), L.dtype_code(act_dtype), _p(stats), _p(mean), _p(rstd), int(training))
+    _call("dx_embed_stats", _p(xs), B, T, V, _p(W0), _p(b0), _p(nobs), _p(run_mean), _p(run_var), _p(stats), _p(mean), _p(rstd),
+          int(training))
+    hn = _embed_hidden(xs, V, W0, b0, nobs, gamma, beta, mean, rstd, act_dtype)
+    psi = torch.empty((B, T + 1, V + 1, d), device=dev, dtype=act_dtype)
+    gemm_(hn, cast(W4, act_dtype), out=_psi_groups(psi, B, T + 1, V, d), bias=b4, act_dtype=act_dtype)
+    _call("dx_embed_special", _p(xs), B, T, V, d, _p(special), _p(tab), _p(psi), L.dtype_code(act_dtype))
     return psi, mean, rstd
 
 
 def embed_bwd(xs, V, d, W0, b0, gamma, beta, W4, nobs, mean, rstd, dpsi, grads, training):
-    """grads: dict with f32 tensors dW0, db0, dgamma, dbeta, dW4, db4, dnobs, dspecial (accumulated). Returns dtab [B,d]."""
+    """grads: dict with f32 tensors dW0, db0, dgamma, dbeta, dW4, db4, dnobs, dspecial (accumulated). Returns dtab [B,d].
+    dpsi is consumed (its special cells are zeroed in place)."""
     B, T, _ = xs.shape
-    dev = xs.device
-    dhn = torch.empty((V, B * T, 64), device=dev, dtype=torch.float32)
-    dgb = torch.empty((2, V, 64), device=dev, dtype=torch.float32)
-    dtab = torch.empty((B, d), device=dev, dtype=torch.float32)
+    T1 = T + 1
+    dev, at = xs.device, dpsi.dtype
     _chk(dpsi)
-    _call("dx_embed_bwd", _p(xs), B, T, V, d, _p(W0), _p(b0), _p(gamma), _p(beta), _p(W4), _p(nobs), _p(mean), _p(rstd),
-          _p(dpsi), _dt(dpsi), _p(dhn), _p(dgb), _p(grads["dW0"]), _p(grads["db0"]), _p(grads["dgamma"]), _p(grads["dbeta"]),
-          _p(grads["dW4"]), _p(grads["db4"]), _p(grads["dnobs"]), _p(grads["dspecial"]), _p(dtab), int(training))
+    dtab = torch.empty((B, d), device=dev, dtype=torch.float32)
+    _call("dx_embed_special_bwd", _p(xs), B, T, V, d, _p(dpsi), _dt(dpsi), _p(grads["dspecial"]), _p(dtab))
+    hn = _embed_hidden(xs, V, W0, b0, nobs, gamma, beta, mean, rstd, at)
+    dv = _psi_groups(dpsi, B, T1, V, d)                                           # [V, B*T1, d]
+    gemm_(dv, hn, a_mn=True, b_mn=True, out=grads["dW4"], accumulate=True)         # dW4[v] += dout_v^T hn_v
+    colsum(dpsi.view(B * T1, (V + 1) * d)[:, :V * d], grads["db4"].view(-1), accumulate=True)
+    dhn = torch.empty((V, B * T1, 64), device=dev, dtype=at)
+    gemm_(dv, cast(W4, at), b_mn=True, out=dhn, act_dtype=at)                      # dhn_v = dout_v W4_v
+    dgb = torch.empty((2, V, 64), device=dev, dtype=torch.float32)
+    _call("dx_embed_bn_reduce", _p(xs), B, T, V, _p(W0), _p(b0), _p(nobs), _p(mean), _p(rstd), _p(dhn), _dt(dhn), _p(dgb))
+    _call("dx_embed_bwd_front", _p(xs), B, T, V, _p(W0), _p(b0), _p(nobs), _p(gamma), _p(mean), _p(rstd), _p(dhn), _dt(dhn),
+          _p(dgb), _p(grads["dW0"]), _p(grads["db0"]), _p(grads["dnobs"]), int(training))
+    axpy(dgb[0], grads["dgamma"], 1.0, accumulate=True)
+    axpy(dgb[1], grads["dbeta"], 1.0, accumulate=True)
     return dtab
 
 
