@@ -124,7 +124,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 struct TcParams {
   int K;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // descriptor byte offsets (test-overridable)
-  int stage_bufs;                        // staging blocks per epilogue warp (STAGED only): 1..3
+  int stage_bufs;                        // staging blocks per epilogue warp (STAGED only), see stage layout below
+  int tiles_m, tiles_n, total_tiles;     // persistent tile loop: tile -> (batch z, m block, n block), n fastest
 };
 
 // ---- warp-staged tile movement (STAGED epilogue) -----------------------------------------------------------
@@ -158,6 +159,29 @@ __device__ __forceinline__ void stage_store(const uint8_t* buf, void* base, long
           *reinterpret_cast<const uint4*>(buf + stg_off(r, piece));
   }
 }
+// asynchronous variant of stage_load (cp.async 16 B, zero-fill out of range): prefetch of the next super-chunk
+__device__ __forceinline__ void stage_load_async(uint8_t* buf, const void* base, long long ld, int m_base, int n0, int M, int N,
+                                                 int lane) {
+  const int piece = lane & 7, rsub = lane >> 3;
+  const int col = n0 + piece * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    const int gm = m_base + r;
+    const bool ok = gm < M && col < N;
+    const bf16* src = reinterpret_cast<const bf16*>(base) + (ok ? ((long long)gm * ld + col) : 0);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(buf + stg_off(r, piece))), "l"(src),
+                 "r"(ok ? 16 : 0)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // this lane's row, one 16 B piece (8 consecutive bf16 columns) as floats / from floats
 __device__ __forceinline__ void stage_piece_get(const uint8_t* buf, int lane, int piece, float (&v)[8]) {
   dx_ld8(reinterpret_cast<const bf16*>(buf + stg_off(lane, piece)), v);
@@ -170,7 +194,9 @@ __device__ __forceinline__ void stage_piece_put(uint8_t* buf, int lane, int piec
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED>
 __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, TcParams p,
-                                                             DxEpi e) {
+                                                             DxEpi e0) {
+  // Persistent CTA: loops over output tiles; the TMA producer and the MMA issuer run ahead of the epilogue warps
+  // through a STAGES-deep operand ring and a 2-deep ring of TMEM accumulators (2*BN columns).
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -179,12 +205,12 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint8_t* stg_base = smem + STAGES * STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, z = blockIdx.z;
   const int num_kb = (p.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -194,11 +220,14 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full_bar + s, 1);
+      mbar_init(tmem_empty_bar + s, 4);   // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -209,25 +238,31 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        uint8_t* sb = sa + A_BYTES;
-        mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
-        const int k0 = kb * BK;
-        if (!A_MN) {
-          tma_load_3d(sa, &tmA, full_bar + s, k0, m0, z);  // box {64 k, 128 m, 1}
-        } else {
+      uint32_t it = 0;   // running k-block counter across tiles
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.tiles_n) * BN;
+        const int m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
+        const int z = tile / (p.tiles_n * p.tiles_m);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_3d(sa, &tmA, full_bar + s, k0, m0, z);  // box {64 k, 128 m, 1}
+          } else {
 #pragma unroll
-          for (int c = 0; c < BM / 64; ++c) tma_load_3d(sa + c * 8192, &tmA, full_bar + s, m0 + c * 64, k0, z);  // {64 m, 64 k, 1}
-        }
-        if (!B_MN) {
-          tma_load_3d(sb, &tmB, full_bar + s, k0, n0, z);  // box {64 k, BN n, 1}
-        } else {
+            for (int c = 0; c < BM / 64; ++c) tma_load_3d(sa + c * 8192, &tmA, full_bar + s, m0 + c * 64, k0, z);  // {64 m, 64 k, 1}
+          }
+          if (!B_MN) {
+            tma_load_3d(sb, &tmB, full_bar + s, k0, n0, z);  // box {64 k, BN n, 1}
+          } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) tma_load_3d(sb + c * 8192, &tmB, full_bar + s, n0 + c * 64, k0, z);
+            for (int c = 0; c < BN / 64; ++c) tma_load_3d(sb + c * 8192, &tmB, full_bar + s, n0 + c * 64, k0, z);
+          }
         }
       }
     }
@@ -238,98 +273,121 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
       // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
                                  ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(full_bar + s, ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t slot = tcount & 1, use = tcount >> 1;
+        mbar_wait(tmem_empty_bar + slot, (use & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+        const uint32_t acc = tmem_base + slot * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle row.
-          // MN-major: advance 16 k-rows = two 1024 B swizzle atoms.
-          const uint64_t ad = make_smem_desc(sa + (A_MN ? k * 2048 : k * 32), p.a_lbo, p.a_sbo);
-          const uint64_t bd = make_smem_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
-          umma_f16(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle row.
+            // MN-major: advance 16 k-rows = two 1024 B swizzle atoms.
+            const uint64_t ad = make_smem_desc(sa + (A_MN ? k * 2048 : k * 32), p.a_lbo, p.a_sbo);
+            const uint64_t bd = make_smem_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
+            umma_f16(acc, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
+        umma_commit(tmem_full_bar + slot);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
     __syncwarp();
   } else {
     // ===== epilogue: warp w reads TMEM lanes [32*(w%4), +32) =====
-    dx_epi_select_batch(e, z);
     const int q = warp & 3;
-    const int m_base = m0 + q * 32;
-    const int m = m_base + lane;
-    const bool row_ok = m < e.M;
-    float rs = 0.f, rd = 0.f;
-    if (!STAGED) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);  // warp-collective
-        if (row_ok) dx_epilogue_chunk<32>(e, m, n0 + c * 32, v, rs, rd);
-      }
-    } else {
-      uint8_t* bufR = stg_base + (warp - 2) * p.stage_bufs * STG_BYTES;  // out (and res, in place)
-      uint8_t* bufX = bufR + STG_BYTES;                                    // aux or cx
-      uint8_t* bufO = bufR + (p.stage_bufs - 1) * STG_BYTES;               // out2 (last block)
-      const bool has_o2 = dx_epi_has_out2(e);
-      const void* xsrc = e.aux ? e.aux : e.cx;
-      const long long xld = e.aux ? e.ldx : e.ldc;
-      bool waited = false;
-#pragma unroll 1
-      for (int sc = 0; sc < BN / 64; ++sc) {
-        const int nc = n0 + sc * 64;
-        if (nc >= e.N) break;
-        // side tensors do not depend on the accumulator: fetch them while the mainloop is still running
-        if (e.res) stage_load(bufR, e.res, e.ldr, m_base, nc, e.M, e.N, lane);
-        if (xsrc) stage_load(bufX, xsrc, xld, m_base, nc, e.M, e.N, lane);
-        __syncwarp();
-        if (!waited) {
-          mbar_wait(tmem_full_bar, 0);
-          tc_fence_after();
-          waited = true;
-        }
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sc * 64 + half * 32), v);  // warp-collective
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int piece = half * 4 + j;
-            const int ncol = nc + piece * 8;
-            float t[8], r[8], a[8], o2[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
-            if (e.res) stage_piece_get(bufR, lane, piece, r);
-            if (xsrc) stage_piece_get(bufX, lane, piece, a);
-            // aux and cx are mutually exclusive in every staged launch: `a` serves as both. N % 8 == 0 -> whole pieces.
-            if (row_ok && ncol < e.N) dx_epilogue_math<8>(e, m, ncol, 8, t, r, a, a, o2, rs, rd);
-            stage_piece_put(bufR, lane, piece, t);
-            if (has_o2) stage_piece_put(bufO, lane, piece, o2);
-          }
-        }
-        __syncwarp();
-        if (e.out) stage_store(bufR, e.out, e.ldo, m_base, nc, e.M, e.N, lane);
-        if (has_o2) stage_store(bufO, e.out2, e.ldo2, m_base, nc, e.M, e.N, lane);
-        __syncwarp();
-      }
-      if (!waited) {  // tile entirely right of N (cannot happen with the host grid, kept for safety)
-        mbar_wait(tmem_full_bar, 0);
+    // staging blocks of this warp (STAGED): [0],[1] = res/out double buffer, [2],[3] = aux|cx double buffer, last = out2
+    uint8_t* wstg = stg_base + (warp - 2) * p.stage_bufs * STG_BYTES;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const int n0 = (tile % p.tiles_n) * BN;
+      const int m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
+      const int z = tile / (p.tiles_n * p.tiles_m);
+      const uint32_t slot = tcount & 1, use = tcount >> 1;
+      const uint32_t acc = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
+      DxEpi e = e0;
+      dx_epi_select_batch(e, z);
+      const int m_base = m0 + q * 32;
+      const int m = m_base + lane;
+      const bool row_ok = m < e.M;
+      float rs = 0.f, rd = 0.f;
+      if (!STAGED) {
+        mbar_wait(tmem_full_bar + slot, use & 1);
         tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tmem_ld32(acc + (uint32_t)(c * 32), v);  // warp-collective
+          if (row_ok) dx_epilogue_chunk<32>(e, m, n0 + c * 32, v, rs, rd);
+        }
+      } else {
+        const bool has_o2 = dx_epi_has_out2(e);
+        const void* xsrc = e.aux ? e.aux : e.cx;
+        const long long xld = e.aux ? e.ldx : e.ldc;
+        uint8_t* bufO = wstg + (p.stage_bufs - 1) * STG_BYTES;
+        const int nsc = min(BN / 64, (e.N - n0 + 63) / 64);
+        // side tensors do not depend on the accumulator: start fetching them while the mainloop is still running
+        if (e.res) stage_load_async(wstg, e.res, e.ldr, m_base, n0, e.M, e.N, lane);
+        if (xsrc) stage_load_async(wstg + 2 * STG_BYTES, xsrc, xld, m_base, n0, e.M, e.N, lane);
+        cp_async_commit();
+        mbar_wait(tmem_full_bar + slot, use & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int sc = 0; sc < nsc; ++sc) {
+          const int nc = n0 + sc * 64;
+          uint8_t* bufR = wstg + (sc & 1) * STG_BYTES;
+          uint8_t* bufX = wstg + (2 + (sc & 1)) * STG_BYTES;
+          if (sc + 1 < nsc) {   // prefetch the next super-chunk into the other buffers
+            if (e.res) stage_load_async(wstg + ((sc + 1) & 1) * STG_BYTES, e.res, e.ldr, m_base, nc + 64, e.M, e.N, lane);
+            if (xsrc) stage_load_async(wstg + (2 + ((sc + 1) & 1)) * STG_BYTES, xsrc, xld, m_base, nc + 64, e.M, e.N, lane);
+            cp_async_commit();
+            cp_async_wait<1>();
+          } else {
+            cp_async_wait<0>();
+          }
+          __syncwarp();
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tmem_ld32(acc + (uint32_t)(sc * 64 + half * 32), v);  // warp-collective
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int piece = half * 4 + j;
+              const int ncol = nc + piece * 8;
+              float t[8], r[8], a[8], o2[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
+              if (e.res) stage_piece_get(bufR, lane, piece, r);
+              if (xsrc) stage_piece_get(bufX, lane, piece, a);
+              // aux and cx are mutually exclusive in every staged launch: `a` serves as both. N % 8 == 0 -> whole pieces.
+              if (row_ok && ncol < e.N) dx_epilogue_math<8>(e, m, ncol, 8, t, r, a, a, o2, rs, rd);
+              stage_piece_put(bufR, lane, piece, t);
+              if (has_o2) stage_piece_put(bufO, lane, piece, o2);
+            }
+          }
+          __syncwarp();
+          if (e.out) stage_store(bufR, e.out, e.ldo, m_base, nc, e.M, e.N, lane);
+          if (has_o2) stage_store(bufO, e.out2, e.ldo2, m_base, nc, e.M, e.N, lane);
+          __syncwarp();
+        }
       }
+      // this warp has finished reading the accumulator: hand the TMEM slot back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+      if (row_ok) dx_epilogue_flush_row(e, m, rs, rd);
     }
-    if (row_ok) dx_epilogue_flush_row(e, m, rs, rd);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -374,14 +432,34 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
                cudaStream_t stream) {
   const int smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/ +
                    (STAGED ? 4 * p.stage_bufs * STG_BYTES : 0);
+  if (smem > 232448) {
+    dx_set_error("dx_gemm_tc: tile config BN=%d stages=%d needs %d B of shared memory", BN, STAGES, smem);
+    return DX_ERR_UNSUPPORTED;
+  }
   auto kern = dx_gemm_tc_kernel<BN, STAGES, A_MN, B_MN, STAGED>;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem = smem;
   }
-  dim3 grid(dx_ceil_div(d->N, BN), dx_ceil_div(d->M, BM), d->batch > 1 ? d->batch : 1);
-  kern<<<grid, NTHREADS, smem, stream>>>(ta, tb, p, e);
+  TcParams pp = p;
+  pp.tiles_n = dx_ceil_div(d->N, BN);
+  pp.tiles_m = dx_ceil_div(d->M, BM);
+  const long long total = (long long)pp.tiles_n * pp.tiles_m * (d->batch > 1 ? d->batch : 1);
+  if (total > 0x7fffffffLL) {
+    dx_set_error("dx_gemm_tc: too many tiles");
+    return DX_ERR_ARG;
+  }
+  pp.total_tiles = (int)total;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    DX_CUDA(cudaGetDevice(&dev));
+    DX_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int ctas_per_sm = smem <= 113 * 1024 ? 2 : 1;   // persistent grid: fill every SM, no more
+  const int grid = (int)(total < (long long)num_sms * ctas_per_sm ? total : (long long)num_sms * ctas_per_sm);
+  kern<<<grid, NTHREADS, smem, stream>>>(ta, tb, pp, e);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }
@@ -391,8 +469,8 @@ int launch_major(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& t
                  const TcParams& p, const DxEpi& e, cudaStream_t stream) {
   if (bn == 256 && stages == 4) return launch_cfg<256, 4, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
   if (bn == 256 && stages == 3) return launch_cfg<256, 3, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
-  if (bn == 128 && stages == 2) return launch_cfg<128, 2, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
   if (bn == 128 && stages == 3) return launch_cfg<128, 3, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
+  if (bn == 128 && stages == 4) return launch_cfg<128, 4, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
   if (bn == 128 && stages == 6) return launch_cfg<128, 6, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
   if (bn == 64 && stages == 4) return launch_cfg<64, 4, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
   dx_set_error("dx_gemm_tc: unsupported tile config BN=%d stages=%d", bn, stages);
@@ -427,15 +505,20 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
   const bool any_side = d->out || d->res || d->aux || d->cx;
   const bool staged = any_side && e.vec_ok && d->act_dtype == DX_BF16 && (!d->out || d->out_dtype == DX_BF16) &&
                       !d->accumulate && (d->N % 8 == 0) && !(d->aux && d->cx);
-  const int nbufs = 1 + ((d->aux || d->cx) ? 1 : 0) + (has_o2 ? 1 : 0);
+  // staging blocks per epilogue warp: res/out double buffer [0,1], aux|cx double buffer [2,3], out2 [last]
+  const int nbufs = staged ? (2 + ((d->aux || d->cx) ? 2 : 0) + (has_o2 ? 1 : 0)) : 0;
   const bool user_cfg = bn > 0;
   if (!user_cfg) {
-    // Heuristic: deep-K contractions get the 128x256 tile; shallow-K (HBM-bound) ones get 128x128 / 2 stages so two
-    // CTAs share an SM; narrow outputs get 128x64.
-    if (d->N <= 64) { bn = 64; stages = 4; }
-    else if (d->K >= 1024 && d->N >= 256) { bn = 256; stages = (staged && nbufs == 3) ? 3 : 4; }
-    else if (d->K >= 1024) { bn = 128; stages = 6; }
-    else { bn = 128; stages = staged ? 2 : 3; }
+    // 128x256 tiles halve the L2 operand re-reads of 128x128 ones (every shape with N >= 256 uses them); narrow outputs get
+    // 128x128 / 128x64.  The operand ring takes the deepest instantiated depth that fits next to the epilogue staging.
+    bn = d->N <= 64 ? 64 : (d->N >= 256 ? 256 : 128);
+    const int budget = 232448 - 1280 - 4 * nbufs * STG_BYTES;
+    const int stage_bytes = (BM + bn) * BK * 2;
+    const int cand[3][3] = {{4, 4, 4}, {6, 4, 3}, {4, 3, 3}};
+    const int* c = cand[bn == 64 ? 0 : (bn == 128 ? 1 : 2)];
+    stages = c[2];
+    for (int i = 0; i < 3; ++i)
+      if (c[i] * stage_bytes <= budget) { stages = c[i]; break; }
   }
   CUtensorMap ta, tb;
   if (!d->a_mn) rc = make_tmap(&ta, d->A, d->K, d->M, d->lda, batch, d->a_bs, BK, BM);
