@@ -138,17 +138,28 @@ __device__ __forceinline__ void dx_epi_store(void* base, long long ld, int dtype
   }
 }
 
+// Per-row constants of the epilogue, loaded / computed once per (tile,row) instead of once per 8-column piece.
+struct DxRowConst {
+  float rs, rs2, coef;
+};
+__device__ __forceinline__ DxRowConst dx_row_const(const DxEpi& e, int m) {
+  DxRowConst c;
+  c.rs = e.row_scale ? e.row_scale[m] : 1.f;
+  c.rs2 = e.row_scale2 ? e.row_scale2[m] : 1.f;
+  c.coef = e.cx ? e.coef_num[m] / fmaxf(e.coef_den[m], 1e-24f) : 0.f;
+  return c;
+}
+
 // Register-only arithmetic of the epilogue.  v: accumulator columns (in) -> final `out` values (out).
 // r / a / c: preloaded residual, aux and cx values (ignored when the corresponding pointer in `e` is null).
 // o2: receives the `out2` values when has_out2() (pre-activation for GELU, unscaled dpre for GELU_BWD).
 template <int CW>
-__device__ __forceinline__ void dx_epilogue_math(const DxEpi& e, int m, int n0, int nvalid, float (&v)[CW],
+__device__ __forceinline__ void dx_epilogue_math(const DxEpi& e, const DxRowConst& rc, int n0, int nvalid, float (&v)[CW],
                                                  const float (&r)[CW], const float (&a)[CW], const float (&c)[CW],
                                                  float (&o2)[CW], float& rs_acc, float& rd_acc) {
   if (e.row_scale) {
-    const float s = e.row_scale[m];
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] *= s;
+    for (int i = 0; i < CW; ++i) v[i] *= rc.rs;
   }
   if (e.bias) {
 #pragma unroll
@@ -174,9 +185,8 @@ __device__ __forceinline__ void dx_epilogue_math(const DxEpi& e, int m, int n0, 
     }
     rd_acc += rd;
     if (e.row_scale2) {
-      const float s2 = e.row_scale2[m];
 #pragma unroll
-      for (int i = 0; i < CW; ++i) v[i] *= s2;
+      for (int i = 0; i < CW; ++i) v[i] *= rc.rs2;
     }
   } else if (e.act == DX_ACT_RELU_BWD) {
 #pragma unroll
@@ -190,9 +200,8 @@ __device__ __forceinline__ void dx_epilogue_math(const DxEpi& e, int m, int n0, 
     for (int i = 0; i < CW; ++i) v[i] += r[i];
   }
   if (e.cx) {
-    const float coef = e.coef_num[m] / fmaxf(e.coef_den[m], 1e-24f);
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] -= c[i] * coef;
+    for (int i = 0; i < CW; ++i) v[i] -= c[i] * rc.coef;
   }
   if (e.row_sumsq) {
     float s = 0.f;
@@ -209,7 +218,8 @@ __device__ __forceinline__ bool dx_epi_has_out2(const DxEpi& e) {
 // Direct-global front-end: applies the epilogue to CW accumulator columns of row m (m < M guaranteed by the caller),
 // 8 columns (one 16 B bf16 vector) at a time to keep the live register set small.
 // rs_acc / rd_acc collect the row reductions; the caller flushes them with one atomicAdd per row.
-__device__ __forceinline__ void dx_epilogue_piece(const DxEpi& e, int m, int n0, float (&v)[8], float& rs_acc, float& rd_acc) {
+__device__ __forceinline__ void dx_epilogue_piece(const DxEpi& e, const DxRowConst& rc, int m, int n0, float (&v)[8],
+                                                  float& rs_acc, float& rd_acc) {
   const int nvalid = min(8, e.N - n0);
   if (nvalid <= 0) return;
   const bool vec = e.vec_ok != 0;
@@ -217,7 +227,7 @@ __device__ __forceinline__ void dx_epilogue_piece(const DxEpi& e, int m, int n0,
   if (e.res) dx_epi_load<8>(e.res, e.ldr, e.act_dtype, m, n0, nvalid, vec, r);
   if (e.aux) dx_epi_load<8>(e.aux, e.ldx, e.act_dtype, m, n0, nvalid, vec, a);
   if (e.cx) dx_epi_load<8>(e.cx, e.ldc, e.act_dtype, m, n0, nvalid, vec, c);
-  dx_epilogue_math<8>(e, m, n0, nvalid, v, r, a, c, o2, rs_acc, rd_acc);
+  dx_epilogue_math<8>(e, rc, n0, nvalid, v, r, a, c, o2, rs_acc, rd_acc);
   if (dx_epi_has_out2(e)) dx_epi_store<8>(e.out2, e.ldo2, e.act_dtype, 0, m, n0, nvalid, vec, o2);
   if (e.out) dx_epi_store<8>(e.out, e.ldo, e.out_dtype, e.accumulate, m, n0, nvalid, vec, v);
 }
@@ -225,12 +235,13 @@ __device__ __forceinline__ void dx_epilogue_piece(const DxEpi& e, int m, int n0,
 template <int CW>
 __device__ __forceinline__ void dx_epilogue_chunk(const DxEpi& e, int m, int n0, float (&v)[CW], float& rs_acc,
                                                   float& rd_acc) {
+  const DxRowConst rc = dx_row_const(e, m);
 #pragma unroll
   for (int i = 0; i < CW; i += 8) {
     float t[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = v[i + j];
-    dx_epilogue_piece(e, m, n0 + i, t, rs_acc, rd_acc);
+    dx_epilogue_piece(e, rc, m, n0 + i, t, rs_acc, rd_acc);
   }
 }
 

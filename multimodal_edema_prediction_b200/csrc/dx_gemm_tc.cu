@@ -6,7 +6,8 @@
 //   `batch` independent problems through the third dimension of the tensor maps.
 //
 // CTA = 128 x BN output tile, BLOCK_K = 64 (one 128 B swizzle row of bf16), STAGES-deep mbarrier ring.
-// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (TMEM lane quadrant = warp % 4; the two
+// warps of a quadrant take alternate 64-column blocks, so every SM scheduler has two epilogue warps to interleave).
 // Large-K shapes use BN=256 (1 CTA per SM, 96 B/clk smem operand traffic per MMA); small-K, HBM-bound shapes use
 // BN=128 with 2 stages so that 2 CTAs share an SM and epilogues overlap mainloops.
 //
@@ -22,7 +23,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int NTHREADS = 192;
+constexpr int NEPI = 8;                 // epilogue warps: 2 per TMEM lane quadrant (they split the column blocks)
+constexpr int NTHREADS = 64 + 32 * NEPI;
 constexpr int STG_BYTES = 32 * 128;   // one staging block: 32 rows x 64 bf16
 
 // ------------------------------------------------------------------------------------------------
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full_bar + s, 1);
-      mbar_init(tmem_empty_bar + s, 4);   // one arrival per epilogue warp
+      mbar_init(tmem_empty_bar + s, NEPI);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -301,9 +303,10 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     }
     __syncwarp();
   } else {
-    // ===== epilogue: warp w reads TMEM lanes [32*(w%4), +32) =====
+    // ===== epilogue: warp w reads TMEM lanes [32*(w%4), +32); column blocks alternate between the quadrant's 2 warps =====
     const int q = warp & 3;
-    // staging blocks of this warp (STAGED): [0],[1] = res/out double buffer, [2],[3] = aux|cx double buffer, last = out2
+    const int chalf = (warp - 2) >> 2;   // 0 or 1
+    // staging blocks of this warp (STAGED): [0] = res -> out (in place), [1] = aux|cx, last = out2
     uint8_t* wstg = stg_base + (warp - 2) * p.stage_bufs * STG_BYTES;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
@@ -317,41 +320,50 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
       const int m_base = m0 + q * 32;
       const int m = m_base + lane;
       const bool row_ok = m < e.M;
+      const DxRowConst rc = row_ok ? dx_row_const(e, m) : DxRowConst{1.f, 1.f, 0.f};
       float rs = 0.f, rd = 0.f;
       if (!STAGED) {
         mbar_wait(tmem_full_bar + slot, use & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = chalf; c < BN / 32; c += 2) {
           float v[32];
           tmem_ld32(acc + (uint32_t)(c * 32), v);  // warp-collective
-          if (row_ok) dx_epilogue_chunk<32>(e, m, n0 + c * 32, v, rs, rd);
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float t[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
+              dx_epilogue_piece(e, rc, m, n0 + c * 32 + j * 8, t, rs, rd);
+            }
+          }
         }
       } else {
         const bool has_o2 = dx_epi_has_out2(e);
         const void* xsrc = e.aux ? e.aux : e.cx;
         const long long xld = e.aux ? e.ldx : e.ldc;
+        uint8_t* bufR = wstg;
+        uint8_t* bufX = wstg + STG_BYTES;
         uint8_t* bufO = wstg + (p.stage_bufs - 1) * STG_BYTES;
         const int nsc = min(BN / 64, (e.N - n0 + 63) / 64);
         // side tensors do not depend on the accumulator: start fetching them while the mainloop is still running
-        if (e.res) stage_load_async(wstg, e.res, e.ldr, m_base, n0, e.M, e.N, lane);
-        if (xsrc) stage_load_async(wstg + 2 * STG_BYTES, xsrc, xld, m_base, n0, e.M, e.N, lane);
+        if (chalf < nsc) {
+          if (e.res) stage_load_async(bufR, e.res, e.ldr, m_base, n0 + chalf * 64, e.M, e.N, lane);
+          if (xsrc) stage_load_async(bufX, xsrc, xld, m_base, n0 + chalf * 64, e.M, e.N, lane);
+        }
         cp_async_commit();
         mbar_wait(tmem_full_bar + slot, use & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int sc = 0; sc < nsc; ++sc) {
+        for (int sc = chalf; sc < nsc; sc += 2) {
           const int nc = n0 + sc * 64;
-          uint8_t* bufR = wstg + (sc & 1) * STG_BYTES;
-          uint8_t* bufX = wstg + (2 + (sc & 1)) * STG_BYTES;
-          if (sc + 1 < nsc) {   // prefetch the next super-chunk into the other buffers
-            if (e.res) stage_load_async(wstg + ((sc + 1) & 1) * STG_BYTES, e.res, e.ldr, m_base, nc + 64, e.M, e.N, lane);
-            if (xsrc) stage_load_async(wstg + (2 + ((sc + 1) & 1)) * STG_BYTES, xsrc, xld, m_base, nc + 64, e.M, e.N, lane);
+          if (sc != chalf) {
+            if (e.res) stage_load_async(bufR, e.res, e.ldr, m_base, nc, e.M, e.N, lane);
+            if (xsrc) stage_load_async(bufX, xsrc, xld, m_base, nc, e.M, e.N, lane);
             cp_async_commit();
-            cp_async_wait<1>();
-          } else {
-            cp_async_wait<0>();
           }
+          cp_async_wait<0>();
           __syncwarp();
 #pragma unroll 1
           for (int half = 0; half < 2; ++half) {
@@ -367,7 +379,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
               if (e.res) stage_piece_get(bufR, lane, piece, r);
               if (xsrc) stage_piece_get(bufX, lane, piece, a);
               // aux and cx are mutually exclusive in every staged launch: `a` serves as both. N % 8 == 0 -> whole pieces.
-              if (row_ok && ncol < e.N) dx_epilogue_math<8>(e, m, ncol, 8, t, r, a, a, o2, rs, rd);
+              if (row_ok && ncol < e.N) dx_epilogue_math<8>(e, rc, ncol, 8, t, r, a, a, o2, rs, rd);
               stage_piece_put(bufR, lane, piece, t);
               if (has_o2) stage_piece_put(bufO, lane, piece, o2);
             }
@@ -431,7 +443,7 @@ template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED>
 int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, const DxEpi& e,
                cudaStream_t stream) {
   const int smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/ +
-                   (STAGED ? 4 * p.stage_bufs * STG_BYTES : 0);
+                   (STAGED ? NEPI * p.stage_bufs * STG_BYTES : 0);
   if (smem > 232448) {
     dx_set_error("dx_gemm_tc: tile config BN=%d stages=%d needs %d B of shared memory", BN, STAGES, smem);
     return DX_ERR_UNSUPPORTED;
@@ -505,14 +517,14 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
   const bool any_side = d->out || d->res || d->aux || d->cx;
   const bool staged = any_side && e.vec_ok && d->act_dtype == DX_BF16 && (!d->out || d->out_dtype == DX_BF16) &&
                       !d->accumulate && (d->N % 8 == 0) && !(d->aux && d->cx);
-  // staging blocks per epilogue warp: res/out double buffer [0,1], aux|cx double buffer [2,3], out2 [last]
-  const int nbufs = staged ? (2 + ((d->aux || d->cx) ? 2 : 0) + (has_o2 ? 1 : 0)) : 0;
+  // staging blocks per epilogue warp: res -> out (in place) [0], aux|cx [1], out2 [last]
+  const int nbufs = staged ? (1 + ((d->aux || d->cx) ? 1 : 0) + (has_o2 ? 1 : 0)) : 0;
   const bool user_cfg = bn > 0;
   if (!user_cfg) {
     // 128x256 tiles halve the L2 operand re-reads of 128x128 ones (every shape with N >= 256 uses them); narrow outputs get
     // 128x128 / 128x64.  The operand ring takes the deepest instantiated depth that fits next to the epilogue staging.
     bn = d->N <= 64 ? 64 : (d->N >= 256 ? 256 : 128);
-    const int budget = 232448 - 1280 - 4 * nbufs * STG_BYTES;
+    const int budget = 232448 - 1280 - NEPI * nbufs * STG_BYTES;
     const int stage_bytes = (BM + bn) * BK * 2;
     const int cand[3][3] = {{4, 4, 4}, {6, 4, 3}, {4, 3, 3}};
     const int* c = cand[bn == 64 ? 0 : (bn == 128 ? 1 : 2)];
