@@ -481,6 +481,7 @@ int launch_major(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& t
                  const TcParams& p, const DxEpi& e, cudaStream_t stream) {
   if (bn == 256 && stages == 4) return launch_cfg<256, 4, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
   if (bn == 256 && stages == 3) return launch_cfg<256, 3, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
+  if (bn == 256 && stages == 2) return launch_cfg<256, 2, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
   if (bn == 128 && stages == 3) return launch_cfg<128, 3, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
   if (bn == 128 && stages == 4) return launch_cfg<128, 4, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
   if (bn == 128 && stages == 6) return launch_cfg<128, 6, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
@@ -526,7 +527,7 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
     bn = d->N <= 64 ? 64 : (d->N >= 256 ? 256 : 128);
     const int budget = 232448 - 1280 - NEPI * nbufs * STG_BYTES;
     const int stage_bytes = (BM + bn) * BK * 2;
-    const int cand[3][3] = {{4, 4, 4}, {6, 4, 3}, {4, 3, 3}};
+    const int cand[3][3] = {{4, 4, 4}, {6, 4, 3}, {4, 3, 2}};
     const int* c = cand[bn == 64 ? 0 : (bn == 128 ? 1 : 2)];
     stages = c[2];
     for (int i = 0; i < 3; ++i)
