@@ -150,6 +150,14 @@ __device__ __forceinline__ DxRowConst dx_row_const(const DxEpi& e, int m) {
   return c;
 }
 
+// split-K partial sums: out (f32) += v with red.global.add (the destination is a gradient accumulator)
+__device__ __forceinline__ void dx_epi_atomic_add8(void* base, long long ld, int m, int n0, int N, const float (&v)[8]) {
+  float* p = reinterpret_cast<float*>(base) + (long long)m * ld + n0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (n0 + i < N) atomicAdd(p + i, v[i]);
+}
+
 // Register-only arithmetic of the epilogue.  v: accumulator columns (in) -> final `out` values (out).
 // r / a / c: preloaded residual, aux and cx values (ignored when the corresponding pointer in `e` is null).
 // o2: receives the `out2` values when has_out2() (pre-activation for GELU, unscaled dpre for GELU_BWD).

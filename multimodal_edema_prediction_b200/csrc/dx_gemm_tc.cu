@@ -127,7 +127,8 @@ struct TcParams {
   int K;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // descriptor byte offsets (test-overridable)
   int stage_bufs;                        // staging blocks per epilogue warp (STAGED only), see stage layout below
-  int tiles_m, tiles_n, total_tiles;     // persistent tile loop: tile -> (batch z, m block, n block), n fastest
+  int tiles_m, tiles_n, total_tiles;     // persistent work loop: unit -> (k split, batch z, m block, n block), n fastest
+  int splits, kb_per_split;              // split-K (dW GEMMs with few output tiles): partial sums are red.add'ed into out
 };
 
 // ---- warp-staged tile movement (STAGED epilogue) -----------------------------------------------------------
@@ -241,11 +242,13 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       // ===== TMA producer =====
       uint32_t it = 0;   // running k-block counter across tiles
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x) {
+        const int tile = unit / p.splits, split = unit - tile * p.splits;
         const int n0 = (tile % p.tiles_n) * BN;
         const int m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
         const int z = tile / (p.tiles_n * p.tiles_m);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int kb_lo = split * p.kb_per_split, kb_hi = min(num_kb, kb_lo + p.kb_per_split);
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(empty_bar + s, ph ^ 1);
@@ -276,12 +279,14 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
                                  ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x, ++tcount) {
+        const int split = unit % p.splits;
+        const int kb_lo = split * p.kb_per_split, kb_hi = min(num_kb, kb_lo + p.kb_per_split);
         const uint32_t slot = tcount & 1, use = tcount >> 1;
         mbar_wait(tmem_empty_bar + slot, (use & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_base + slot * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(full_bar + s, ph);
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
             // MN-major: advance 16 k-rows = two 1024 B swizzle atoms.
             const uint64_t ad = make_smem_desc(sa + (A_MN ? k * 2048 : k * 32), p.a_lbo, p.a_sbo);
             const uint64_t bd = make_smem_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
-            umma_f16(acc, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_f16(acc, ad, bd, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
         }
@@ -309,7 +314,8 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     // staging blocks of this warp (STAGED): [0] = res -> out (in place), [1] = aux|cx, last = out2
     uint8_t* wstg = stg_base + (warp - 2) * p.stage_bufs * STG_BYTES;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+    for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x, ++tcount) {
+      const int tile = unit / p.splits;
       const int n0 = (tile % p.tiles_n) * BN;
       const int m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
       const int z = tile / (p.tiles_n * p.tiles_m);
@@ -335,7 +341,8 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
               float t[8];
 #pragma unroll
               for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
-              dx_epilogue_piece(e, rc, m, n0 + c * 32 + j * 8, t, rs, rd);
+              if (p.splits > 1) dx_epi_atomic_add8(e.out, e.ldo, m, n0 + c * 32 + j * 8, e.N, t);
+              else dx_epilogue_piece(e, rc, m, n0 + c * 32 + j * 8, t, rs, rd);
             }
           }
         }
@@ -457,18 +464,34 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   TcParams pp = p;
   pp.tiles_n = dx_ceil_div(d->N, BN);
   pp.tiles_m = dx_ceil_div(d->M, BM);
-  const long long total = (long long)pp.tiles_n * pp.tiles_m * (d->batch > 1 ? d->batch : 1);
-  if (total > 0x7fffffffLL) {
-    dx_set_error("dx_gemm_tc: too many tiles");
-    return DX_ERR_ARG;
-  }
-  pp.total_tiles = (int)total;
+  long long total = (long long)pp.tiles_n * pp.tiles_m * (d->batch > 1 ? d->batch : 1);
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     DX_CUDA(cudaGetDevice(&dev));
     DX_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  // split-K: only for pure fp32 accumulation (dW += A^T B) when the output tiles cannot fill the machine
+  pp.splits = 1;
+  const int num_kb = dx_ceil_div(d->K, BK);
+  const bool pure_acc = d->accumulate && d->out_dtype == DX_F32 && !d->out2 && !d->res && !d->aux && !d->cx && !d->bias &&
+                        !d->row_scale && !d->row_sumsq && !d->row_dot && d->act == DX_ACT_NONE;
+  if (!STAGED && pure_acc && total < num_sms && num_kb >= 32) {
+    double best = (double)total / num_sms;
+    for (int sp = 2; sp <= 16 && num_kb / sp >= 16; ++sp) {
+      const long long u = total * sp;
+      const double eff = (double)u / ((double)((u + num_sms - 1) / num_sms) * num_sms);
+      if (eff > best + 0.04) { best = eff; pp.splits = sp; }
+    }
+  }
+  pp.kb_per_split = dx_ceil_div(num_kb, pp.splits);
+  pp.splits = dx_ceil_div(num_kb, pp.kb_per_split);
+  total *= pp.splits;
+  if (total > 0x7fffffffLL) {
+    dx_set_error("dx_gemm_tc: too many tiles");
+    return DX_ERR_ARG;
+  }
+  pp.total_tiles = (int)total;
   const int ctas_per_sm = smem <= 113 * 1024 ? 2 : 1;   // persistent grid: fill every SM, no more
   const int grid = (int)(total < (long long)num_sms * ctas_per_sm ? total : (long long)num_sms * ctas_per_sm);
   kern<<<grid, NTHREADS, smem, stream>>>(ta, tb, pp, e);
