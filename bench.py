@@ -222,8 +222,10 @@ def main():
             ops.PROFILE = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         for i in range(steps):
             fn(i)
+        timed.host_ms = (time.perf_counter() - h0) * 1e3 / steps     # host enqueue time per step (no sync inside)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -238,6 +240,7 @@ def main():
         step_resident(i)
     clocks = ClockSampler(local) if rank == 0 else None
     ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    host_ms = timed.host_ms
     clk = clocks.stop() if clocks else None
     for i in range(3):
         step_e2e(i)
@@ -288,7 +291,7 @@ def main():
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
             "model_tflops": value * train_flops_per_sample() / 1e12,
             "model_frac_of_bf16_peak": value * train_flops_per_sample() / 1e12 / (world * pk["bf16_tflops_sustained"]),
-            "allreduce_buckets_per_step": red.launched,
+            "allreduce_buckets_per_step": red.launched, "host_enqueue_ms_per_step": host_ms,
         }
         print(json.dumps(out))
     if world > 1:

@@ -79,6 +79,9 @@ typedef struct dx_gemm_desc {
   int64_t a_bs, b_bs, out_bs, out2_bs, res_bs, aux_bs, cx_bs;
   int32_t bias_bs;                   /* stride of bias / aux_bias between batches */
   int32_t rowvec_bs;                 /* stride of the [M] row vectors (row_scale, coef_num, row_sumsq, ...) between batches */
+  int32_t split_k;                   /* FFMA kernel only: >1 splits K over blockIdx.z; needs accumulate into a zeroed f32 out,
+                                        plain epilogue (bias allowed).  The tcgen05 kernel picks its own split for dW GEMMs. */
+  int32_t reserved;
 } dx_gemm_desc;
 
 int dx_gemm(const dx_gemm_desc* d, void* stream);
@@ -156,13 +159,15 @@ int dx_embed_bwd_front(const float* xs, int B, int T, int V, const float* W0, co
 /* BatchNormLastDim on [R,C] f32 (duett/duett.py:11-22; tab_encoder, cve, head) and LayerNorm on [R,C]
  * (models/main_architecture_duett.py:745-774).  Backward accumulates dw/db; dx may be NULL. */
 int dx_bn2d_fwd(const float* x, int R, int C, const float* w, const float* b, float* run_mean, float* run_var, float* y,
-                float* mean, float* rstd, int training, void* stream);
+                float* mean, float* rstd, double* stats_ws /* [C,2] */, int training, void* stream);
 int dx_bn2d_bwd(const float* dy, const float* x, int R, int C, const float* w, const float* mean, const float* rstd,
-                float* dx, float* dw, float* db, int training, void* stream);
+                float* dx, float* dw, float* db, float* ws /* [C,2] */, int training, void* stream);
 int dx_layernorm_fwd(const void* x, int R, int C, const float* w, const float* b, void* y, float* mean, float* rstd,
                      int dtype, void* stream);
 int dx_layernorm_bwd(const void* dy, const void* x, int R, int C, const float* w, const float* mean, const float* rstd,
                      void* dx, float* dw, float* db, int dtype, void* stream);
+/* out = act(x) for act in DX_ACT_{GELU,RELU,TANH} (activation after a split-K GEMM, whose epilogue cannot apply it). */
+int dx_act_fwd(const void* x, void* out, int64_t n, int act, int dtype, void* stream);
 /* out = g * act'(aux), act in DX_ACT_{GELU,RELU,TANH}_BWD. */
 int dx_act_bwd(const void* g, const void* aux, void* out, int64_t n, int act, int dtype, void* stream);
 

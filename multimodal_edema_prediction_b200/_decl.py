@@ -22,8 +22,8 @@ SIGNATURES = {
     "dx_embed_special_bwd": [P, I, I, I, I, P, I, P, P, P],
     "dx_embed_bn_reduce": [P, I, I, I, P, P, P, P, P, P, I, P, P],
     "dx_embed_bwd_front": [P, I, I, I, P, P, P, P, P, P, P, I, P, P, P, P, I, P],
-    "dx_bn2d_fwd": [P, I, I, P, P, P, P, P, P, P, I, P],
-    "dx_bn2d_bwd": [P, P, I, I, P, P, P, P, P, P, I, P],
+    "dx_bn2d_fwd": [P, I, I, P, P, P, P, P, P, P, P, I, P],
+    "dx_bn2d_bwd": [P, P, I, I, P, P, P, P, P, P, P, I, P],
     "dx_layernorm_fwd": [P, I, I, P, P, P, P, P, I, P],
     "dx_layernorm_bwd": [P, P, I, I, P, P, P, P, P, P, I, P],
     "dx_kd_loss": [P, P, P, I, F, F, F, F, P, P, P],
@@ -39,6 +39,7 @@ SIGNATURES = {
     "dx_sumsq": [P, L, P, P],
     "dx_clip_factor": [P, F, P, P],
     "dx_act_bwd": [P, P, P, L, I, I, P],
+    "dx_act_fwd": [P, P, L, I, I, P],
     "dx_fusion_logits": [P, P, P, P, P, P, P, P, P, P, I, I, P],
     "dx_fusion_logits_bwd": [P, P, P, P, P, P, P, P, P, P, I, I, P],
     "dx_scale_dev": [P, P, P, L, I, P],

@@ -39,11 +39,39 @@ __device__ __forceinline__ void load_tile(float* sm, const AttnView& v, int b, i
   }
 }
 
+// 16 B shared-memory reads: a key/value row slice of DHT floats is consumed as DHT/4 LDS.128 (every DHT is a multiple of 4)
+template <int DHT>
+__device__ __forceinline__ float dot4(const float (&q)[DHT], const float* __restrict__ k) {
+  const float4* k4 = reinterpret_cast<const float4*>(k);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < DHT / 4; ++i) {
+    const float4 kk = k4[i];
+    s = fmaf(q[4 * i], kk.x, s);
+    s = fmaf(q[4 * i + 1], kk.y, s);
+    s = fmaf(q[4 * i + 2], kk.z, s);
+    s = fmaf(q[4 * i + 3], kk.w, s);
+  }
+  return s;
+}
+template <int DHT>
+__device__ __forceinline__ void axpy4(float (&acc)[DHT], float p, const float* __restrict__ v) {
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+#pragma unroll
+  for (int i = 0; i < DHT / 4; ++i) {
+    const float4 vv = v4[i];
+    acc[4 * i] = fmaf(p, vv.x, acc[4 * i]);
+    acc[4 * i + 1] = fmaf(p, vv.y, acc[4 * i + 1]);
+    acc[4 * i + 2] = fmaf(p, vv.z, acc[4 * i + 2]);
+    acc[4 * i + 3] = fmaf(p, vv.w, acc[4 * i + 3]);
+  }
+}
+
 template <typename T, int DH, int TPQ>
 __global__ void __launch_bounds__(NTH) attn_fwd_kernel(AttnView q, AttnView k, AttnView v, AttnViewW o, float* lse,
                                                       int H, int Sq, int Sk, float scale) {
   constexpr int DHT = DH / TPQ;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* sk = smem;
   float* sv = smem + KT * DH;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -65,9 +93,7 @@ __global__ void __launch_bounds__(NTH) attn_fwd_kernel(AttnView q, AttnView k, A
     const int kn = min(KT, Sk - k0);
     for (int j = 0; j < kn; ++j) {
       const float* kj = sk + j * DH + part * DHT;
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < DHT; ++i) s = fmaf(qr[i], kj[i], s);
+      float s = dot4<DHT>(qr, kj);
 #pragma unroll
       for (int off = 1; off < TPQ; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
       if (s > m) {
@@ -79,9 +105,7 @@ __global__ void __launch_bounds__(NTH) attn_fwd_kernel(AttnView q, AttnView k, A
       }
       const float p = __expf(s - m);
       l += p;
-      const float* vj = sv + j * DH + part * DHT;
-#pragma unroll
-      for (int i = 0; i < DHT; ++i) acc[i] = fmaf(p, vj[i], acc[i]);
+      axpy4<DHT>(acc, p, sv + j * DH + part * DHT);
     }
   }
   if (active) {
@@ -99,7 +123,7 @@ __global__ void __launch_bounds__(NTH) attn_bwd_q_kernel(AttnView q, AttnView k,
                                                         AttnViewW dq, const float* lse, float* Dv, int H, int Sq, int Sk,
                                                         float scale) {
   constexpr int DHT = DH / TPQ;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* sk = smem;
   float* sv = smem + KT * DH;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -129,20 +153,14 @@ __global__ void __launch_bounds__(NTH) attn_bwd_q_kernel(AttnView q, AttnView k,
     for (int j = 0; j < kn; ++j) {
       const float* kj = sk + j * DH + part * DHT;
       const float* vj = sv + j * DH + part * DHT;
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int i = 0; i < DHT; ++i) {
-        s = fmaf(qr[i], kj[i], s);
-        dp = fmaf(gr[i], vj[i], dp);
-      }
+      float s = dot4<DHT>(qr, kj), dp = dot4<DHT>(gr, vj);
 #pragma unroll
       for (int off = 1; off < TPQ; off <<= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, off);
         dp += __shfl_xor_sync(0xffffffffu, dp, off);
       }
       const float ds = __expf(s - L) * (dp - D);
-#pragma unroll
-      for (int i = 0; i < DHT; ++i) acc[i] = fmaf(ds, kj[i], acc[i]);
+      axpy4<DHT>(acc, ds, kj);
     }
   }
   if (active) {
@@ -159,7 +177,7 @@ __global__ void __launch_bounds__(NTH) attn_bwd_kv_kernel(AttnView q, AttnView k
                                                          AttnViewW dv, const float* lse, const float* Dv, int H, int Sq,
                                                          int Sk, float scale) {
   constexpr int DHT = DH / TPQ;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* sq = smem;
   float* sg = smem + KT * DH;
   float* sl = smem + 2 * KT * DH;  // lse tile
@@ -191,12 +209,7 @@ __global__ void __launch_bounds__(NTH) attn_bwd_kv_kernel(AttnView q, AttnView k
     for (int i2 = 0; i2 < qn; ++i2) {
       const float* qi = sq + i2 * DH + part * DHT;
       const float* gi = sg + i2 * DH + part * DHT;
-      float s = 0.f, dp = 0.f;
-#pragma unroll
-      for (int i = 0; i < DHT; ++i) {
-        s = fmaf(qi[i], kr[i], s);
-        dp = fmaf(gi[i], vr[i], dp);
-      }
+      float s = dot4<DHT>(kr, qi), dp = dot4<DHT>(vr, gi);
 #pragma unroll
       for (int off = 1; off < TPQ; off <<= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -204,11 +217,8 @@ __global__ void __launch_bounds__(NTH) attn_bwd_kv_kernel(AttnView q, AttnView k
       }
       const float p = __expf(s * scale - sl[i2]);
       const float ds = p * (dp - sd[i2]);
-#pragma unroll
-      for (int i = 0; i < DHT; ++i) {
-        av[i] = fmaf(p, gi[i], av[i]);
-        ak[i] = fmaf(ds, qi[i], ak[i]);
-      }
+      axpy4<DHT>(av, p, gi);
+      axpy4<DHT>(ak, ds, qi);
     }
   }
   if (active) {

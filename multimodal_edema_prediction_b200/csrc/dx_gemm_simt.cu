@@ -1,6 +1,9 @@
 // fp32 FFMA GEMM with the shared fused epilogue.  This is the fp32 precision mode's contraction kernel
-// (parity at 1e-3 against the CPU oracle needs true fp32 products; tcgen05 kind::tf32 would not give it)
-// and the on-device cross-check for the tcgen05 kernel.  Tile 64x128x16, 256 threads, 4x8 micro-tile.
+// (parity at 1e-3 against the CPU oracle needs true fp32 products; tcgen05 kind::tf32 would not give it),
+// the kernel of the small fp32 MLPs around the backbone (tab_encoder, cve front, heads) and the on-device cross-check
+// for the tcgen05 kernel.  Tile 64x128x16, 256 threads, 4x8 micro-tile.
+// blockIdx.z = batch index (grouped mode) or K-split index (split_k > 1: skinny outputs with a huge K such as the
+// [B, (V+1)d] x [(V+1)d, 64] head projection; partial sums are red.add'ed into a zero-initialised fp32 output).
 #include "dx_gemm_epilogue.cuh"
 
 namespace {
@@ -10,10 +13,17 @@ constexpr int BM = 64, BN = 128, BK = 16, NT = 256;
 template <typename TI>
 __global__ void __launch_bounds__(NT) dx_gemm_simt_kernel(const TI* __restrict__ A, long long sam, long long sak,
                                                          const TI* __restrict__ B, long long sbn, long long sbk,
-                                                         int K, DxEpi e, long long a_bs, long long b_bs) {
-  A += (long long)blockIdx.z * a_bs;
-  B += (long long)blockIdx.z * b_bs;
-  dx_epi_select_batch(e, blockIdx.z);
+                                                         int K, DxEpi e, long long a_bs, long long b_bs, int splits) {
+  int k_lo = 0, k_hi = K;
+  if (splits > 1) {
+    const int per = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+    k_lo = blockIdx.z * per;
+    k_hi = min(K, k_lo + per);
+  } else {
+    A += (long long)blockIdx.z * a_bs;
+    B += (long long)blockIdx.z * b_bs;
+    dx_epi_select_batch(e, blockIdx.z);
+  }
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int t = threadIdx.x;
@@ -26,7 +36,7 @@ __global__ void __launch_bounds__(NT) dx_gemm_simt_kernel(const TI* __restrict__
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   const bool a_kmajor = (sak == 1), b_kmajor = (sbk == 1);
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
     // A tile: BM*BK = 1024 elements, 4 per thread
 #pragma unroll
     for (int i = 0; i < (BM * BK) / NT; ++i) {
@@ -35,7 +45,7 @@ __global__ void __launch_bounds__(NT) dx_gemm_simt_kernel(const TI* __restrict__
       if (a_kmajor) { k = idx % BK; m = idx / BK; } else { m = idx % BM; k = idx / BM; }
       const int gm = m0 + m, gk = k0 + k;
       float v = 0.f;
-      if (gm < e.M && gk < K) v = dx_ld(A + (long long)gm * sam + (long long)gk * sak);
+      if (gm < e.M && gk < k_hi) v = dx_ld(A + (long long)gm * sam + (long long)gk * sak);
       As[k][m] = v;
     }
 #pragma unroll
@@ -45,7 +55,7 @@ __global__ void __launch_bounds__(NT) dx_gemm_simt_kernel(const TI* __restrict__
       if (b_kmajor) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
       const int gn = n0 + n, gk = k0 + k;
       float v = 0.f;
-      if (gn < e.N && gk < K) v = dx_ld(B + (long long)gn * sbn + (long long)gk * sbk);
+      if (gn < e.N && gk < k_hi) v = dx_ld(B + (long long)gn * sbn + (long long)gk * sbk);
       Bs[k][n] = v;
     }
     __syncthreads();
@@ -67,9 +77,18 @@ __global__ void __launch_bounds__(NT) dx_gemm_simt_kernel(const TI* __restrict__
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;
     if (m >= e.M) continue;
+    const int nn = n0 + tx * 8;
+    if (splits > 1) {
+      if (blockIdx.z == 0 && e.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += (nn + j < e.N) ? e.bias[nn + j] : 0.f;
+      }
+      dx_epi_atomic_add8(e.out, e.ldo, m, nn, e.N, acc[i]);
+      continue;
+    }
     float rs = 0.f, rd = 0.f;
-    dx_epilogue_chunk<8>(e, m, n0 + tx * 8, acc[i], rs, rd);
-    if (n0 + tx * 8 < e.N) dx_epilogue_flush_row(e, m, rs, rd);
+    dx_epilogue_chunk<8>(e, m, nn, acc[i], rs, rd);
+    if (nn < e.N) dx_epilogue_flush_row(e, m, rs, rd);
   }
 }
 
@@ -79,13 +98,22 @@ int dx_gemm_simt_launch(const dx_gemm_desc* d, cudaStream_t stream) {
   DxEpi e = dx_make_epi(d);
   const long long sam = d->a_mn ? 1 : d->lda, sak = d->a_mn ? d->lda : 1;
   const long long sbn = d->b_mn ? 1 : d->ldb, sbk = d->b_mn ? d->ldb : 1;
-  dim3 grid(dx_ceil_div(d->N, BN), dx_ceil_div(d->M, BM), d->batch > 1 ? d->batch : 1);
+  const int batch = d->batch > 1 ? d->batch : 1;
+  int splits = d->split_k > 1 ? d->split_k : 1;
+  if (splits > 1) {
+    DX_CHECK_ARG(batch == 1 && d->accumulate && d->out && d->out_dtype == DX_F32 && !d->out2 && !d->res && !d->aux && !d->cx &&
+                     !d->row_scale && !d->row_sumsq && !d->row_dot && d->act == DX_ACT_NONE,
+                 "dx_gemm: split_k needs a plain fp32 accumulate epilogue (bias allowed), batch == 1");
+    const int per = ((d->K + splits - 1) / splits + BK - 1) / BK * BK;
+    splits = (d->K + per - 1) / per;
+  }
+  dim3 grid(dx_ceil_div(d->N, BN), dx_ceil_div(d->M, BM), splits > 1 ? splits : batch);
   if (d->in_dtype == DX_F32) {
     dx_gemm_simt_kernel<float><<<grid, NT, 0, stream>>>((const float*)d->A, sam, sak, (const float*)d->B, sbn, sbk,
-                                                        d->K, e, d->a_bs, d->b_bs);
+                                                        d->K, e, d->a_bs, d->b_bs, splits);
   } else {
     dx_gemm_simt_kernel<bf16><<<grid, NT, 0, stream>>>((const bf16*)d->A, sam, sak, (const bf16*)d->B, sbn, sbk,
-                                                       d->K, e, d->a_bs, d->b_bs);
+                                                       d->K, e, d->a_bs, d->b_bs, splits);
   }
   DX_LAUNCH_CHECK();
   return DX_OK;

@@ -228,6 +228,26 @@ int dx_scale_dev(const float* x, const float* s, float* out, int64_t n, int ns, 
   return DX_OK;
 }
 
+extern "C++" {
+template <typename T>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, long long n, int act) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float v = dx_ld(x + i);
+    dx_st(out + i, act == DX_ACT_RELU ? fmaxf(v, 0.f) : (act == DX_ACT_TANH ? tanhf(v) : dx_gelu(v)));
+  }
+}
+}  // extern "C++"
+
+int dx_act_fwd(const void* x, void* out, int64_t n, int act, int dtype, void* stream) {
+  DX_CHECK_ARG(x && out && n > 0 && act >= DX_ACT_GELU && act <= DX_ACT_TANH, "dx_act_fwd: bad arguments");
+  long long g = (n + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  if (dtype == DX_BF16) act_fwd_kernel<bf16><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, n, act);
+  else act_fwd_kernel<float><<<(int)g, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)out, n, act);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
 /* sink[0] += (sum_i x[i]) / g[0]   — ScaleNorm gain gradient from the per-row dots (backbone.py) */
 __global__ void __launch_bounds__(256) sum_div_acc_kernel(const float* __restrict__ x, long long n, const float* __restrict__ g,
                                                          float* __restrict__ sink) {

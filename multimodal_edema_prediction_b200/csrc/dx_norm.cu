@@ -9,87 +9,119 @@ namespace {
 constexpr float BN_EPS = 1e-5f;
 constexpr float LN_EPS = 1e-5f;
 
-// block = 32 channels x 8 row lanes
-__global__ void __launch_bounds__(256) bn2d_fwd_kernel(const float* __restrict__ x, int R, int C, const float* __restrict__ w,
-                                                      const float* __restrict__ b, float* __restrict__ run_mean,
-                                                      float* __restrict__ run_var, float* __restrict__ y,
-                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int training) {
-  __shared__ double sh[2][8][32];
-  __shared__ float smean[32], srstd[32];
+// Two launches each way so that small-C problems still fill the machine: (1) partial sums over row chunks
+// (grid = channel tiles x row chunks, atomics into a [C,2] workspace), (2) apply.  block = 32 channels x 8 row lanes.
+__global__ void __launch_bounds__(256) bn2d_stats_kernel(const float* __restrict__ x, int R, int C, int rows_per_block,
+                                                        double* __restrict__ ws) {
+  __shared__ float sh[2][8][32];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  const bool ok = c < C;
-  if (training) {
-    double s = 0, ss = 0;
-    if (ok)
-      for (int r = rl; r < R; r += 8) {
-        const double v = x[(long long)r * C + c];
-        s += v;
-        ss += v * v;
-      }
-    sh[0][rl][cl] = s;
-    sh[1][rl][cl] = ss;
-    __syncthreads();
-    if (rl == 0 && ok) {
-      s = 0; ss = 0;
-      for (int i = 0; i < 8; ++i) { s += sh[0][i][cl]; ss += sh[1][i][cl]; }
-      const double m = s / R;
-      double var = ss / R - m * m;
-      if (var < 0) var = 0;
-      smean[cl] = (float)m;
-      srstd[cl] = (float)(1.0 / sqrt(var + (double)BN_EPS));
-      if (run_mean) {
-        const double unb = R > 1 ? var * R / (R - 1) : var;
-        run_mean[c] = 0.9f * run_mean[c] + 0.1f * (float)m;
-        run_var[c] = 0.9f * run_var[c] + 0.1f * (float)unb;
-      }
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  float s = 0.f, ss = 0.f;
+  if (c < C)
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const float v = x[(long long)r * C + c];
+      s += v;
+      ss = fmaf(v, v, ss);
     }
-  } else if (rl == 0 && ok) {
-    smean[cl] = run_mean[c];
-    srstd[cl] = rsqrtf(run_var[c] + BN_EPS);
-  }
+  sh[0][rl][cl] = s;
+  sh[1][rl][cl] = ss;
   __syncthreads();
-  if (!ok) return;
-  const float m = smean[cl], rs = srstd[cl], ww = w[c], bb = b[c];
-  if (rl == 0) { mean_out[c] = m; rstd_out[c] = rs; }
-  for (int r = rl; r < R; r += 8) y[(long long)r * C + c] = (x[(long long)r * C + c] - m) * rs * ww + bb;
+  if (rl == 0 && c < C) {
+    s = 0.f; ss = 0.f;
+    for (int i = 0; i < 8; ++i) { s += sh[0][i][cl]; ss += sh[1][i][cl]; }
+    atomicAdd(ws + 2 * c, (double)s);
+    atomicAdd(ws + 2 * c + 1, (double)ss);
+  }
 }
 
-__global__ void __launch_bounds__(256) bn2d_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int R, int C,
-                                                      const float* __restrict__ w, const float* __restrict__ mean,
-                                                      const float* __restrict__ rstd, float* __restrict__ dx,
-                                                      float* __restrict__ dw, float* __restrict__ db, int training) {
-  __shared__ float sh[2][8][32];
-  __shared__ float s1[32], s2[32];
+__global__ void __launch_bounds__(256) bn2d_apply_kernel(const float* __restrict__ x, int R, int C, int rows_per_block,
+                                                        const double* __restrict__ ws, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float* __restrict__ run_mean,
+                                                        float* __restrict__ run_var, float* __restrict__ y,
+                                                        float* __restrict__ mean_out, float* __restrict__ rstd_out, int training) {
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  const bool ok = c < C;
-  const float m = ok ? mean[c] : 0.f, rs = ok ? rstd[c] : 0.f, ww = ok ? w[c] : 0.f;
-  float a = 0.f, bsum = 0.f;
-  if (ok)
-    for (int r = rl; r < R; r += 8) {
-      const float g = dy[(long long)r * C + c];
-      const float xh = (x[(long long)r * C + c] - m) * rs;
-      a += g;
-      bsum = fmaf(g, xh, bsum);
+  if (c >= C) return;
+  float m, rs;
+  if (training) {
+    const double mm = ws[2 * c] / R;
+    double var = ws[2 * c + 1] / R - mm * mm;
+    if (var < 0) var = 0;
+    m = (float)mm;
+    rs = (float)(1.0 / sqrt(var + (double)BN_EPS));
+    if (blockIdx.y == 0 && rl == 0 && run_mean) {
+      const double unb = R > 1 ? var * R / (R - 1) : var;
+      run_mean[c] = 0.9f * run_mean[c] + 0.1f * m;
+      run_var[c] = 0.9f * run_var[c] + 0.1f * (float)unb;
     }
+  } else {
+    m = run_mean[c];
+    rs = rsqrtf(run_var[c] + BN_EPS);
+  }
+  if (blockIdx.y == 0 && rl == 0) { mean_out[c] = m; rstd_out[c] = rs; }
+  const float ww = w[c], bb = b[c];
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  for (int r = r0 + rl; r < r1; r += 8) y[(long long)r * C + c] = (x[(long long)r * C + c] - m) * rs * ww + bb;
+}
+
+// ws[c] = {sum dy, sum dy*xhat}
+__global__ void __launch_bounds__(256) bn2d_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, int R, int C,
+                                                             int rows_per_block, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, float* __restrict__ ws) {
+  __shared__ float sh[2][8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  float a = 0.f, bsum = 0.f;
+  if (c < C) {
+    const float m = mean[c], rs = rstd[c];
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const float g = dy[(long long)r * C + c];
+      a += g;
+      bsum = fmaf(g, (x[(long long)r * C + c] - m) * rs, bsum);
+    }
+  }
   sh[0][rl][cl] = a;
   sh[1][rl][cl] = bsum;
   __syncthreads();
-  if (rl == 0) {
+  if (rl == 0 && c < C) {
     a = 0.f; bsum = 0.f;
     for (int i = 0; i < 8; ++i) { a += sh[0][i][cl]; bsum += sh[1][i][cl]; }
-    s1[cl] = a; s2[cl] = bsum;
-    if (ok) { atomicAdd(db + c, a); atomicAdd(dw + c, bsum); }
+    atomicAdd(ws + 2 * c, a);
+    atomicAdd(ws + 2 * c + 1, bsum);
   }
-  __syncthreads();
-  if (!ok || !dx) return;
-  const float mg = training ? s1[cl] / R : 0.f, mgx = training ? s2[cl] / R : 0.f;
-  for (int r = rl; r < R; r += 8) {
+}
+
+__global__ void __launch_bounds__(256) bn2d_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x, int R, int C,
+                                                            int rows_per_block, const float* __restrict__ w,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ ws, float* __restrict__ dx,
+                                                            float* __restrict__ dw, float* __restrict__ db, int training) {
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  if (c >= C) return;
+  const float s1 = ws[2 * c], s2 = ws[2 * c + 1];
+  if (blockIdx.y == 0 && rl == 0) { atomicAdd(db + c, s1); atomicAdd(dw + c, s2); }
+  if (!dx) return;
+  const float m = mean[c], rs = rstd[c], ww = w[c];
+  const float mg = training ? s1 / R : 0.f, mgx = training ? s2 / R : 0.f;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  for (int r = r0 + rl; r < r1; r += 8) {
     const float g = dy[(long long)r * C + c];
     const float xh = (x[(long long)r * C + c] - m) * rs;
     dx[(long long)r * C + c] = ww * rs * (g - mg - xh * mgx);
   }
+}
+
+static inline int bn_chunks(int R, int C, int& rpb) {
+  const int ct = (C + 31) / 32;
+  int nch = (2 * 148 + ct - 1) / ct;
+  if (nch > (R + 63) / 64) nch = (R + 63) / 64;
+  if (nch < 1) nch = 1;
+  rpb = (R + nch - 1) / nch;
+  rpb = ((rpb + 7) / 8) * 8;
+  return (R + rpb - 1) / rpb;
 }
 
 // LayerNorm: one warp per row
@@ -158,19 +190,36 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
 extern "C" {
 
 int dx_bn2d_fwd(const float* x, int R, int C, const float* w, const float* b, float* run_mean, float* run_var, float* y,
-                float* mean, float* rstd, int training, void* stream) {
+                float* mean, float* rstd, double* stats_ws, int training, void* stream) {
   DX_CHECK_ARG(x && w && b && y && mean && rstd && R > 0 && C > 0, "dx_bn2d_fwd: bad arguments");
   DX_CHECK_ARG(training || (run_mean && run_var), "dx_bn2d_fwd: eval mode needs running statistics");
-  bn2d_fwd_kernel<<<dx_ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(x, R, C, w, b, run_mean, run_var, y, mean, rstd, training);
+  DX_CHECK_ARG(!training || stats_ws, "dx_bn2d_fwd: training mode needs the [C,2] double workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rpb;
+  const int nch = bn_chunks(R, C, rpb);
+  dim3 grid((C + 31) / 32, nch);
+  if (training) {
+    DX_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * C, st));
+    bn2d_stats_kernel<<<grid, 256, 0, st>>>(x, R, C, rpb, stats_ws);
+    DX_LAUNCH_CHECK();
+  }
+  bn2d_apply_kernel<<<grid, 256, 0, st>>>(x, R, C, rpb, stats_ws, w, b, run_mean, run_var, y, mean, rstd, training);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }
 
-/* dw, db are accumulated; dx may be NULL. */
+/* dw, db are accumulated; dx may be NULL. ws: [C,2] f32 scratch. */
 int dx_bn2d_bwd(const float* dy, const float* x, int R, int C, const float* w, const float* mean, const float* rstd,
-                float* dx, float* dw, float* db, int training, void* stream) {
-  DX_CHECK_ARG(dy && x && w && mean && rstd && dw && db, "dx_bn2d_bwd: bad arguments");
-  bn2d_bwd_kernel<<<dx_ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(dy, x, R, C, w, mean, rstd, dx, dw, db, training);
+                float* dx, float* dw, float* db, float* ws, int training, void* stream) {
+  DX_CHECK_ARG(dy && x && w && mean && rstd && dw && db && ws, "dx_bn2d_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rpb;
+  const int nch = bn_chunks(R, C, rpb);
+  dim3 grid((C + 31) / 32, nch);
+  DX_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, st));
+  bn2d_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dy, x, R, C, rpb, mean, rstd, ws);
+  DX_LAUNCH_CHECK();
+  bn2d_bwd_apply_kernel<<<grid, 256, 0, st>>>(dy, x, R, C, rpb, w, mean, rstd, ws, dx, dw, db, training);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }

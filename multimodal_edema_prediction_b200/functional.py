@@ -41,11 +41,22 @@ class LinearFn(torch.autograd.Function):
         Wc = ops.cast(weight.detach(), x2.dtype)
         if x2.dtype == torch.bfloat16 and K % 8:
             raise ops.L.DxError(f"bf16 Linear needs in_features % 8 == 0 (got {K})")
-        y = torch.empty((x2.shape[0], N), device=x.device, dtype=x2.dtype)
-        pre = torch.empty_like(y) if act == ops.ACT_GELU else None
+        M = x2.shape[0]
         r2 = None if res is None else _dense2d(res, N)
-        ops.gemm_(x2, Wc, out=y, out2=pre, bias=None if bias is None else bias.detach(), act=act, res=r2,
-                  act_dtype=x2.dtype)
+        split = 0
+        if x2.dtype == torch.float32 and res is None and K >= 2048 and ((M + 63) // 64) * ((N + 127) // 128) <= 32:
+            split = min(64, K // 256)          # skinny output, huge K (pooled features -> head): spread K over the SMs
+        if split > 1:
+            pre = torch.zeros((M, N), device=x.device, dtype=torch.float32)
+            ops.gemm_(x2, Wc, out=pre, bias=None if bias is None else bias.detach(), accumulate=True, split_k=split)
+            y = pre if act == ops.ACT_NONE else ops.act_fwd(pre, act)
+            if act != ops.ACT_GELU:
+                pre = None
+        else:
+            y = torch.empty((M, N), device=x.device, dtype=x2.dtype)
+            pre = torch.empty_like(y) if act == ops.ACT_GELU else None
+            ops.gemm_(x2, Wc, out=y, out2=pre, bias=None if bias is None else bias.detach(), act=act, res=r2,
+                      act_dtype=x2.dtype)
         ctx.act, ctx.lead, ctx.has_bias, ctx.has_res = act, x.shape[:-1], bias is not None, res is not None
         aux = pre if pre is not None else y
         if act != ops.ACT_NONE and res is not None:

@@ -233,7 +233,8 @@ def bn2d_fwd(x, w, b, run_mean, run_var, training):
     y = torch.empty_like(x)
     mean = torch.empty(Cc, device=x.device, dtype=torch.float32)
     rstd = torch.empty(Cc, device=x.device, dtype=torch.float32)
-    _call("dx_bn2d_fwd", _p(x), R, Cc, _p(w), _p(b), _p(run_mean), _p(run_var), _p(y), _p(mean), _p(rstd), int(training))
+    ws = torch.empty((Cc, 2), device=x.device, dtype=torch.float64) if training else None
+    _call("dx_bn2d_fwd", _p(x), R, Cc, _p(w), _p(b), _p(run_mean), _p(run_var), _p(y), _p(mean), _p(rstd), _p(ws), int(training))
     return y, mean, rstd
 
 
@@ -241,7 +242,8 @@ def bn2d_bwd(dy, x, w, mean, rstd, dw, db, training, need_dx=True):
     _chk(dy, torch.float32)
     R, Cc = x.shape
     dx = torch.empty_like(x) if need_dx else None
-    _call("dx_bn2d_bwd", _p(dy), _p(x), R, Cc, _p(w), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), int(training))
+    ws = torch.empty((Cc, 2), device=x.device, dtype=torch.float32)
+    _call("dx_bn2d_bwd", _p(dy), _p(x), R, Cc, _p(w), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), _p(ws), int(training))
     return dx
 
 
@@ -344,6 +346,14 @@ def aux_residual_kl(img_logits, scaled_corr, y, mask, eps=0.05, need_grad=True):
 def require_device(t):
     if not t.is_cuda:
         raise L.DxError("duett_b200 has no CPU path: inputs must be CUDA tensors on a B200")
+
+
+def act_fwd(x, act):
+    """act(x) for ACT_GELU / ACT_RELU / ACT_TANH (after a split-K GEMM, whose epilogue cannot apply the activation)."""
+    _chk(x)
+    out = torch.empty_like(x)
+    _call("dx_act_fwd", _p(x), _p(out), x.numel(), act, _dt(x))
+    return out
 
 
 def act_bwd(g, aux, act_bwd_code):

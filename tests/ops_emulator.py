@@ -29,10 +29,19 @@ def _gelu_grad(x):
 
 def gemm_(a, b, *, a_mn=False, b_mn=False, out=None, out2=None, accumulate=False, act=ACT_NONE, act_dtype=None,
           row_scale=None, row_scale2=None, bias=None, res=None, aux=None, aux_bias=None, cx=None, coef_num=None,
-          coef_den=None, row_sumsq=None, row_dot=None, force_simt=False):
-    A = a.float().t() if a_mn else a.float()
-    Bm = b.float().t() if b_mn else b.float()
-    v = A @ Bm.t()
+          coef_den=None, row_sumsq=None, row_dot=None, force_simt=False, split_k=0):
+    A = a.float().transpose(-1, -2) if a_mn else a.float()
+    Bm = b.float().transpose(-1, -2) if b_mn else b.float()
+    v = A @ Bm.transpose(-1, -2)
+    if v.dim() == 3:      # grouped mode: plain / bias / accumulate epilogues only (what the embedding uses)
+        assert act == ACT_NONE and res is None and cx is None and aux is None and row_scale is None
+        if bias is not None:
+            v = v + bias[:, None, :]
+        if accumulate:
+            out += v
+        else:
+            out.copy_(v)
+        return
     if row_scale is not None:
         v = v * row_scale[:, None]
     if bias is not None:
@@ -354,6 +363,12 @@ def require_device(t):
     pass
 
 
+def act_fwd(x, act):
+    xf = x.float()
+    r = torch.relu(xf) if act == ACT_RELU else (torch.tanh(xf) if act == ACT_TANH else F.gelu(xf))
+    return r.to(x.dtype)
+
+
 def act_bwd(g, aux, code):
     a, gg = aux.float(), g.float()
     if code == ACT_RELU_BWD:
@@ -413,7 +428,7 @@ def clip_factor(sumsq_t, max_norm, clip):
 EMULATED = ["gemm_", "relayout_fwd", "relayout_bwd", "colsum", "axpy", "axpy_f32", "cast", "scalenorm_scale", "rowdot_scale",
             "attn_fwd", "attn_bwd", "embed_fwd", "embed_bwd", "bn2d_fwd", "bn2d_bwd", "layernorm_fwd", "layernorm_bwd",
             "mean_rows", "mean_rows_bwd", "gather_vec", "scatter_vec", "kd_loss", "bce_logits", "masked_mse_bce",
-            "masked_bce_cols", "aux_residual_kl", "require_device", "act_bwd", "scale_dev", "sum_div_acc", "fusion_logits",
+            "masked_bce_cols", "aux_residual_kl", "require_device", "act_bwd", "act_fwd", "scale_dev", "sum_div_acc", "fusion_logits",
             "fusion_logits_bwd", "adamw", "sumsq", "clip_factor"]
 
 
