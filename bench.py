@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=16, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-out", default=None, help="write the per-shape GEMM timing table to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -191,7 +192,7 @@ def main():
         dev_batches.append((x, hb["y"].to(device)))
     torch.cuda.synchronize()
 
-    def step_resident(i):
+    def step_eager(i):
         x, y = dev_batches[i % nb]
         opt.zero_grad()
         red.start_step()
@@ -201,13 +202,51 @@ def main():
         opt.step(grad_scale=red.finish())
         return loss
 
-    def step_e2e(i):
-        hb = host[i % nb]
+    # ---- whole-step CUDA graph (forward + loss + backward + all-reduce + AdamW), inputs copied into static tensors -----
+    x0, y0 = dev_batches[0]
+    static = {"xs_static": x0[0].clone(), "xs_ts": x0[1].clone(), "xs_times": x0[2].clone(), "y": y0.clone()}
+    n_steps_static = x0[3]
+
+    def train_fn():
         opt.zero_grad()
         red.start_step()
-        loss = model.training_step(((hb["x_ts"], hb["x_static"], list(hb["bin_ends"])), hb["y"]), i)
+        y_hat = model.forward((static["xs_static"], static["xs_ts"], static["xs_times"], n_steps_static))
+        loss = model._supervised_loss(y_hat, static["y"])
         loss.backward()
         opt.step(grad_scale=red.finish())
+        return loss
+
+    gstep, graph_err = None, None
+    if not args.no_graph:
+        try:
+            from multimodal_edema_prediction_b200.graph import CudaGraphStep
+            launches_before = ops.launches()
+            gstep = CudaGraphStep(train_fn, static, warmup=max(args.warmup, 3))
+            launches_per_graph = (ops.launches() - launches_before) // (max(args.warmup, 3) + 1)
+        except Exception as ex:          # capture unsupported in this configuration: run eagerly and say so
+            graph_err, gstep = repr(ex)[:200], None
+            torch.cuda.synchronize()
+
+    def step_resident(i):
+        if gstep is None:
+            return step_eager(i)
+        x, y = dev_batches[i % nb]
+        return gstep(xs_static=x[0], xs_ts=x[1], xs_times=x[2], y=y)
+
+    y_host = [tuple(hb["y"].tolist()) for hb in host]
+
+    def step_e2e(i):
+        hb = host[i % nb]
+        if gstep is None:
+            opt.zero_grad()
+            red.start_step()
+            loss = model.training_step(((hb["x_ts"], hb["x_static"], list(hb["bin_ends"])), y_host[i % nb]), i)
+            loss.backward()
+            opt.step(grad_scale=red.finish())
+            return float(loss)                          # device -> host read of the step's result
+        # host collate format -> pinned staging -> device (Model.feats_to_input), then the captured step
+        xs_static, xs_ts, xs_times, _ = model.feats_to_input((hb["x_ts"], hb["x_static"], list(hb["bin_ends"])), B)
+        loss = gstep(xs_static=xs_static, xs_ts=xs_ts, xs_times=xs_times, y=hb["y"])
         return float(loss)                              # device -> host read of the step's result
 
     def barrier():
@@ -239,9 +278,15 @@ def main():
     for i in range(args.warmup):
         step_resident(i)
     clocks = ClockSampler(local) if rank == 0 else None
-    ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    ms, launches, _ = timed(step_resident, args.steps)
     host_ms = timed.host_ms
     clk = clocks.stop() if clocks else None
+    if gstep is not None:
+        launches = launches_per_graph * args.steps       # kernels replayed from the graph in the timed region
+    # per-GEMM CUDA-event timing needs eager launches (events cannot bracket nodes of a replayed graph)
+    for i in range(2):
+        step_eager(i)
+    ms_eager, _, prof = timed(step_eager, args.steps, profile=True)
     for i in range(3):
         step_e2e(i)
     ms_e2e, _, _ = timed(step_e2e, args.steps)
@@ -268,7 +313,8 @@ def main():
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "kernel": "dx_gemm_tc_kernel (tcgen05, all launches)",
                 "launches_per_step": len(tc) / args.steps, "flops_per_launch": tot_fl / max(len(tc), 1),
-                "ms_per_launch": tot_ms / max(len(tc), 1), "share_of_step": tot_ms / ms, "peak_source": pk["source"]}
+                "ms_per_launch": tot_ms / max(len(tc), 1), "share_of_step": tot_ms / ms, "peak_source": pk["source"],
+                "timed_in": "eager pass of the same step, K steps, CUDA events around every launch"}
         # ---- CPU baseline (oracle port on this box's host cores, bounded sample) ----------------------------------------
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -292,6 +338,7 @@ def main():
             "model_tflops": value * train_flops_per_sample() / 1e12,
             "model_frac_of_bf16_peak": value * train_flops_per_sample() / 1e12 / (world * pk["bf16_tflops_sustained"]),
             "allreduce_buckets_per_step": red.launched, "host_enqueue_ms_per_step": host_ms,
+            "cuda_graph": gstep is not None, "cuda_graph_error": graph_err, "eager_ms_per_step": ms_eager / args.steps,
         }
         print(json.dumps(out))
     if world > 1:

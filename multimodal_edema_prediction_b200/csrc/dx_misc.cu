@@ -79,8 +79,15 @@ __global__ void __launch_bounds__(NT) scatter_vec_kernel(const float* __restrict
 __global__ void __launch_bounds__(NT) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                   float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                   float wd, float bc1, float bc2, const float* __restrict__ gscale_ptr,
-                                                  float gscale) {
+                                                  float gscale, const int* __restrict__ step_dev,
+                                                  const float* __restrict__ lr_scale_dev) {
   const float gs = gscale_ptr ? gscale_ptr[0] * gscale : gscale;
+  if (step_dev) {   // CUDA-graph friendly: the step counter (hence the bias correction) lives on the device
+    const float st = (float)step_dev[0];
+    bc1 = 1.f - powf(b1, st);
+    bc2 = 1.f - powf(b2, st);
+  }
+  if (lr_scale_dev) lr *= lr_scale_dev[0];
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
     const float gi = g[i] * gs;
     float pi = p[i];
@@ -297,11 +304,12 @@ int dx_fusion_logits_bwd(const float* d_img, const float* d_ts, const float* d_s
 
 /* AdamW step on flat f32 buffers. Effective gradient = g * grad_scale * (grad_scale_dev ? *grad_scale_dev : 1). */
 int dx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-             float weight_decay, int step, const float* grad_scale_dev, float grad_scale, void* stream) {
-  DX_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "dx_adamw: bad arguments");
-  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+             float weight_decay, int step, const float* grad_scale_dev, float grad_scale, const int* step_dev,
+             const float* lr_scale_dev, void* stream) {
+  DX_CHECK_ARG(p && g && m && v && n > 0 && (step >= 1 || step_dev), "dx_adamw: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)(step >= 1 ? step : 1)), bc2 = 1.f - powf(beta2, (float)(step >= 1 ? step : 1));
   adamw_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
-                                                             grad_scale_dev, grad_scale);
+                                                             grad_scale_dev, grad_scale, step_dev, lr_scale_dev);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }

@@ -132,6 +132,9 @@ class FusedAdamW:
         self.max_grad_norm = max_grad_norm
         self._ss = torch.zeros(1, device=flat.data.device)
         self._clip = torch.ones(1, device=flat.data.device)
+        # device-resident step counter and LR multiplier: a captured CUDA graph of step() stays valid as they advance
+        self.step_dev = torch.zeros(1, device=flat.data.device, dtype=torch.int32)
+        self.lr_scale_dev = torch.ones(1, device=flat.data.device)
         # contiguous runs of identical (lr_scale, wd)
         cfg = []
         for n in flat.names:
@@ -153,8 +156,13 @@ class FusedAdamW:
     def zero_grad(self, set_to_none=False):
         self.flat.zero_grad()
 
+    def set_lr_scale(self, scale: float):
+        """LR-schedule multiplier (warm-up / cosine / inv-sqrt), applied on the device."""
+        self.lr_scale_dev.fill_(float(scale))
+
     def step(self, grad_scale=1.0, lr=None):
         self.step_count += 1
+        self.step_dev.add_(1)
         lr = self.lr if lr is None else lr
         clip = None
         if self.max_grad_norm is not None:
@@ -166,4 +174,5 @@ class FusedAdamW:
         f = self.flat
         for lo, hi, s, wd in self.runs:
             ops.adamw(f.data[lo:hi], f.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], lr * s, self.betas, self.eps, wd,
-                      self.step_count, grad_scale_dev=clip, grad_scale=grad_scale)
+                      self.step_count, grad_scale_dev=clip, grad_scale=grad_scale, step_dev=self.step_dev,
+                      lr_scale_dev=self.lr_scale_dev)

@@ -397,11 +397,12 @@ def fusion_logits_bwd(d_img, d_ts, d_scaled, d_fus, corr, beta, dbeta, dbias_i, 
 
 
 # ---- optimizer -------------------------------------------------------------------------------------------------------------
-def adamw(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale_dev=None, grad_scale=1.0):
+def adamw(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale_dev=None, grad_scale=1.0, step_dev=None,
+          lr_scale_dev=None):
     for t in (p, g, m, v):
         _chk(t, torch.float32)
     _call("dx_adamw", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
-          float(weight_decay), int(step), _p(grad_scale_dev), float(grad_scale))
+          float(weight_decay), int(step), _p(grad_scale_dev), float(grad_scale), _p(step_dev), _p(lr_scale_dev))
 
 
 def sumsq(x, out):

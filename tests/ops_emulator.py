@@ -407,7 +407,12 @@ def fusion_logits_bwd(d_img, d_ts, d_scaled, d_fus, corr, beta, dbeta, dbias_i, 
     return gs * beta[None]
 
 
-def adamw(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale_dev=None, grad_scale=1.0):
+def adamw(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale_dev=None, grad_scale=1.0, step_dev=None,
+          lr_scale_dev=None):
+    if step_dev is not None:
+        step = int(step_dev[0])
+    if lr_scale_dev is not None:
+        lr = lr * float(lr_scale_dev[0])
     gs = grad_scale * (float(grad_scale_dev[0]) if grad_scale_dev is not None else 1.0)
     gi = g * gs
     p.mul_(1 - lr * weight_decay)
