@@ -18,12 +18,11 @@ class CudaGraphStep:
     def __init__(self, fn, static_inputs: dict, warmup: int = 3):
         self.fn, self.static = fn, static_inputs
         self.graph = None
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):           # warm-up off the capture: lazy allocations, cudaFuncSetAttribute, autotuning
-            for _ in range(warmup):
-                self.out = fn()
-        torch.cuda.current_stream().wait_stream(s)
+        # Warm-up on the CURRENT stream (lazy allocations, cudaFuncSetAttribute).  The usual side-stream warm-up makes the
+        # autograd engine record cross-stream dependencies on the flat gradient buffer, which a later capture rejects
+        # ("dependency created on uncaptured work in another stream").
+        for _ in range(warmup):
+            self.out = fn()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

@@ -36,7 +36,7 @@ def _ref_keyed_grads(module):
     return sd
 
 
-def _grad_check(got, want, tol, floor=5e-2, selfdev=None):
+def _grad_check(got, want, tol, floor=1e-1, selfdev=None):
     """fp32 mode / oracle comparisons: per tensor ||got-want|| <= tol*||want|| + floor*tol*max|grad|*sqrt(numel) (the
     floor covers cancellation-dominated gradients such as a bias feeding tanh->BatchNorm or a ScaleNorm gain under a
     scale-invariant BatchNorm head, whose magnitude is 1e-3 of their siblings).
