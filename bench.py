@@ -224,6 +224,8 @@ def main():
             gstep = CudaGraphStep(train_fn, static, warmup=max(args.warmup, 3))
             launches_per_graph = (ops.launches() - launches_before) // (max(args.warmup, 3) + 1)
         except Exception as ex:          # capture unsupported in this configuration: run eagerly and say so
+            import traceback
+            traceback.print_exc(file=sys.stderr)
             graph_err, gstep = repr(ex)[:200], None
             torch.cuda.synchronize()
 

@@ -22,7 +22,8 @@ class CudaGraphStep:
         # autograd engine record cross-stream dependencies on the flat gradient buffer, which a later capture rejects
         # ("dependency created on uncaptured work in another stream").
         for _ in range(warmup):
-            self.out = fn()
+            out = fn()
+        del out                          # no eager autograd graph may be released in the middle of the capture
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
