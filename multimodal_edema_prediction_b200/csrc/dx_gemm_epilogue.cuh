@@ -153,6 +153,11 @@ __device__ __forceinline__ DxRowConst dx_row_const(const DxEpi& e, int m) {
 // split-K partial sums: out (f32) += v with red.global.add (the destination is a gradient accumulator)
 __device__ __forceinline__ void dx_epi_atomic_add8(void* base, long long ld, int m, int n0, int N, const float (&v)[8]) {
   float* p = reinterpret_cast<float*>(base) + (long long)m * ld + n0;
+  if (n0 + 8 <= N && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {   // red.global.add.v4.f32
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+    atomicAdd(reinterpret_cast<float4*>(p + 4), make_float4(v[4], v[5], v[6], v[7]));
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if (n0 + i < N) atomicAdd(p + i, v[i]);
@@ -215,6 +220,79 @@ __device__ __forceinline__ void dx_epilogue_math(const DxEpi& e, const DxRowCons
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < CW; ++i) s += (i < nvalid) ? v[i] * v[i] : 0.f;
+    rs_acc += s;
+  }
+}
+
+// Compile-time specialised arithmetic: MASK is a bit set of the features a launch uses (the host computes it once), so the
+// per-piece code has no feature branches.  Every combination the DuETT path produces has an instantiation in
+// dx_gemm_tc.cu; anything else falls back to the runtime-flag version above.
+enum : int { DX_M_RS = 1, DX_M_BIAS = 2, DX_M_GELU = 4, DX_M_RES = 8, DX_M_ROWSQ = 16, DX_M_CX = 32, DX_M_GELUBWD = 64 };
+
+static inline int dx_epi_mask(const dx_gemm_desc* d) {
+  // returns -1 when the launch uses a feature combination without a specialisation
+  int m = 0;
+  if (d->row_scale) m |= DX_M_RS;
+  if (d->bias) m |= DX_M_BIAS;
+  if (d->res) m |= DX_M_RES;
+  if (d->row_sumsq) m |= DX_M_ROWSQ;
+  if (d->cx) m |= DX_M_CX;
+  if (d->act == DX_ACT_GELU) { if (!d->out2) return -1; m |= DX_M_GELU; }
+  else if (d->act == DX_ACT_GELU_BWD) { if (!d->out2 || !d->aux_bias || !d->row_scale2 || !d->row_dot) return -1; m |= DX_M_GELUBWD; }
+  else if (d->act != DX_ACT_NONE) return -1;
+  else if (d->aux || d->row_scale2 || d->row_dot) return -1;
+  switch (m) {
+    case 0: case DX_M_BIAS: case DX_M_RS: case DX_M_RS | DX_M_BIAS | DX_M_GELU: case DX_M_RES | DX_M_ROWSQ:
+    case DX_M_BIAS | DX_M_RES | DX_M_ROWSQ: case DX_M_GELUBWD: case DX_M_RES | DX_M_CX:
+      return m;
+    default:
+      return -1;
+  }
+}
+
+template <int MASK>
+__device__ __forceinline__ void dx_epilogue_math_c(const DxEpi& e, const DxRowConst& rc, int n0, float (&v)[8], const float (&r)[8],
+                                                   const float (&a)[8], float (&o2)[8], float& rs_acc, float& rd_acc) {
+  if constexpr ((MASK & DX_M_RS) != 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= rc.rs;
+  }
+  if constexpr ((MASK & DX_M_BIAS) != 0) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + n0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if constexpr ((MASK & DX_M_GELU) != 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o2[i] = v[i]; v[i] = dx_gelu(v[i]); }
+  }
+  if constexpr ((MASK & DX_M_GELUBWD) != 0) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.aux_bias + n0));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.aux_bias + n0 + 4));
+    const float ab[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float rd = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] *= dx_gelu_grad(a[i]);
+      rd = fmaf(v[i], a[i] - ab[i], rd);
+      o2[i] = v[i];
+      v[i] *= rc.rs2;
+    }
+    rd_acc += rd;
+  }
+  if constexpr ((MASK & DX_M_RES) != 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += r[i];
+  }
+  if constexpr ((MASK & DX_M_CX) != 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(-a[i], rc.coef, v[i]);
+  }
+  if constexpr ((MASK & DX_M_ROWSQ) != 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(v[i], v[i], s);
     rs_acc += s;
   }
 }

@@ -129,6 +129,7 @@ struct TcParams {
   int stage_bufs;                        // staging blocks per epilogue warp (STAGED only), see stage layout below
   int tiles_m, tiles_n, total_tiles;     // persistent work loop: unit -> (k split, batch z, m block, n block), n fastest
   int splits, kb_per_split;              // split-K (dW GEMMs with few output tiles): partial sums are red.add'ed into out
+  int epi_mask;                          // staged epilogue: compile-time feature mask (dx_epi_mask), -1 = runtime flags
 };
 
 // ---- warp-staged tile movement (STAGED epilogue) -----------------------------------------------------------
@@ -136,30 +137,19 @@ struct TcParams {
 // conflict-free both for the row-per-lane view (epilogue math) and for the 8-lanes-per-row view (global traffic).
 __device__ __forceinline__ uint32_t stg_off(int r, int p) { return (uint32_t)(r * 128 + ((p ^ (r & 7)) << 4)); }
 
-__device__ __forceinline__ void stage_load(uint8_t* buf, const void* base, long long ld, int m_base, int n0, int M, int N,
-                                           int lane) {
-  const int piece = lane & 7, rsub = lane >> 3;
-  const int col = n0 + piece * 8;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rsub;
-    const int gm = m_base + r;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (gm < M && col < N) val = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + (long long)gm * ld + col));
-    *reinterpret_cast<uint4*>(buf + stg_off(r, piece)) = val;
-  }
-}
 __device__ __forceinline__ void stage_store(const uint8_t* buf, void* base, long long ld, int m_base, int n0, int M, int N,
                                             int lane) {
   const int piece = lane & 7, rsub = lane >> 3;
   const int col = n0 + piece * 8;
+  if (col >= N) return;
+  bf16* gp = reinterpret_cast<bf16*>(base) + (long long)(m_base + rsub) * ld + col;
+  const long long gstep = 4 * ld;
+  const uint8_t* sp = buf + rsub * 128;
+  const uint32_t pe = (uint32_t)((piece ^ rsub) << 4), po = (uint32_t)((piece ^ (rsub + 4)) << 4);
+  const int rows = M - m_base - rsub;   // rows r = 4*i + rsub valid while 4*i < rows
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rsub;
-    const int gm = m_base + r;
-    if (gm < M && col < N)
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + (long long)gm * ld + col) =
-          *reinterpret_cast<const uint4*>(buf + stg_off(r, piece));
+    if (4 * i < rows) *reinterpret_cast<uint4*>(gp + i * gstep) = *reinterpret_cast<const uint4*>(sp + i * 512 + ((i & 1) ? po : pe));
   }
 }
 // asynchronous variant of stage_load (cp.async 16 B, zero-fill out of range): prefetch of the next super-chunk
@@ -167,14 +157,17 @@ __device__ __forceinline__ void stage_load_async(uint8_t* buf, const void* base,
                                                  int lane) {
   const int piece = lane & 7, rsub = lane >> 3;
   const int col = n0 + piece * 8;
+  const bool col_ok = col < N;
+  const bf16* gp = reinterpret_cast<const bf16*>(base) + (col_ok ? ((long long)(m_base + rsub) * ld + col) : 0);
+  const long long gstep = col_ok ? 4 * ld : 0;
+  const uint32_t sp = smem_u32(buf) + rsub * 128;
+  const uint32_t pe = (uint32_t)((piece ^ rsub) << 4), po = (uint32_t)((piece ^ (rsub + 4)) << 4);
+  const int rows = col_ok ? (M - m_base - rsub) : 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rsub;
-    const int gm = m_base + r;
-    const bool ok = gm < M && col < N;
-    const bf16* src = reinterpret_cast<const bf16*>(base) + (ok ? ((long long)gm * ld + col) : 0);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(buf + stg_off(r, piece))), "l"(src),
-                 "r"(ok ? 16 : 0)
+    const bool ok = 4 * i < rows;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sp + i * 512 + ((i & 1) ? po : pe)),
+                 "l"(ok ? gp + i * gstep : gp), "r"(ok ? 16 : 0)
                  : "memory");
   }
 }
@@ -185,12 +178,70 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// this lane's row, one 16 B piece (8 consecutive bf16 columns) as floats / from floats
-__device__ __forceinline__ void stage_piece_get(const uint8_t* buf, int lane, int piece, float (&v)[8]) {
-  dx_ld8(reinterpret_cast<const bf16*>(buf + stg_off(lane, piece)), v);
-}
-__device__ __forceinline__ void stage_piece_put(uint8_t* buf, int lane, int piece, const float (&v)[8]) {
-  dx_st8(reinterpret_cast<bf16*>(buf + stg_off(lane, piece)), v);
+// One output tile of the staged epilogue for the calling epilogue warp.  MASK >= 0: compile-time feature set; -1: runtime.
+template <int BN, int MASK>
+__device__ __forceinline__ void staged_tile(const DxEpi& e, const DxRowConst& rc, uint32_t acc, uint8_t* wstg, int stage_bufs,
+                                            int m_base, bool row_ok, int n0, int chalf, int lane, uint64_t* full_bar,
+                                            uint32_t parity, float& rs, float& rd) {
+  constexpr bool CT = MASK >= 0;
+  const bool has_res = CT ? ((MASK & DX_M_RES) != 0) : (e.res != nullptr);
+  const bool has_x = CT ? ((MASK & (DX_M_CX | DX_M_GELUBWD)) != 0) : (e.aux != nullptr || e.cx != nullptr);
+  const bool has_o2 = CT ? ((MASK & (DX_M_GELU | DX_M_GELUBWD)) != 0) : dx_epi_has_out2(e);
+  const void* xsrc = e.aux ? e.aux : e.cx;
+  const long long xld = e.aux ? e.ldx : e.ldc;
+  uint8_t* bufR = wstg;
+  uint8_t* bufX = wstg + STG_BYTES;
+  uint8_t* bufO = wstg + (stage_bufs - 1) * STG_BYTES;
+  const int nsc = min(BN / 64, (e.N - n0 + 63) / 64);
+  // side tensors do not depend on the accumulator: start fetching them while the mainloop is still running
+  if (chalf < nsc) {
+    if (has_res) stage_load_async(bufR, e.res, e.ldr, m_base, n0 + chalf * 64, e.M, e.N, lane);
+    if (has_x) stage_load_async(bufX, xsrc, xld, m_base, n0 + chalf * 64, e.M, e.N, lane);
+  }
+  cp_async_commit();
+  mbar_wait(full_bar, parity);
+  tc_fence_after();
+  const uint32_t lsw = (uint32_t)(lane & 7);
+  uint8_t* rowR = bufR + lane * 128;
+  const uint8_t* rowX = bufX + lane * 128;
+  uint8_t* rowO = bufO + lane * 128;
+#pragma unroll 1
+  for (int sc = chalf; sc < nsc; sc += 2) {
+    const int nc = n0 + sc * 64;
+    if (sc != chalf) {
+      if (has_res) stage_load_async(bufR, e.res, e.ldr, m_base, nc, e.M, e.N, lane);
+      if (has_x) stage_load_async(bufX, xsrc, xld, m_base, nc, e.M, e.N, lane);
+      cp_async_commit();
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float v[32];
+      tmem_ld32(acc + (uint32_t)(sc * 64 + half * 32), v);  // warp-collective
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int piece = half * 4 + j;
+        const uint32_t po = ((uint32_t)piece ^ lsw) << 4;
+        const int ncol = nc + piece * 8;
+        float t[8], r[8], a[8], o2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
+        if (has_res) dx_ld8(reinterpret_cast<const bf16*>(rowR + po), r);
+        if (has_x) dx_ld8(reinterpret_cast<const bf16*>(rowX + po), a);
+        if (row_ok && ncol < e.N) {   // N % 8 == 0 on this path: pieces are whole
+          if constexpr (CT) dx_epilogue_math_c<MASK>(e, rc, ncol, t, r, a, o2, rs, rd);
+          else dx_epilogue_math<8>(e, rc, ncol, 8, t, r, a, a, o2, rs, rd);   // aux and cx are mutually exclusive: `a` is both
+        }
+        dx_st8(reinterpret_cast<bf16*>(rowR + po), t);
+        if (has_o2) dx_st8(reinterpret_cast<bf16*>(rowO + po), o2);
+      }
+    }
+    __syncwarp();
+    if (e.out) stage_store(bufR, e.out, e.ldo, m_base, nc, e.M, e.N, lane);
+    if (has_o2) stage_store(bufO, e.out2, e.ldo2, m_base, nc, e.M, e.N, lane);
+    __syncwarp();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -347,55 +398,19 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
           }
         }
       } else {
-        const bool has_o2 = dx_epi_has_out2(e);
-        const void* xsrc = e.aux ? e.aux : e.cx;
-        const long long xld = e.aux ? e.ldx : e.ldc;
-        uint8_t* bufR = wstg;
-        uint8_t* bufX = wstg + STG_BYTES;
-        uint8_t* bufO = wstg + (p.stage_bufs - 1) * STG_BYTES;
-        const int nsc = min(BN / 64, (e.N - n0 + 63) / 64);
-        // side tensors do not depend on the accumulator: start fetching them while the mainloop is still running
-        if (chalf < nsc) {
-          if (e.res) stage_load_async(bufR, e.res, e.ldr, m_base, n0 + chalf * 64, e.M, e.N, lane);
-          if (xsrc) stage_load_async(bufX, xsrc, xld, m_base, n0 + chalf * 64, e.M, e.N, lane);
+#define DX_TILE(MASKV) staged_tile<BN, MASKV>(e, rc, acc, wstg, p.stage_bufs, m_base, row_ok, n0, chalf, lane, tmem_full_bar + slot, use & 1, rs, rd)
+        switch (p.epi_mask) {
+          case 0: DX_TILE(0); break;
+          case DX_M_BIAS: DX_TILE(DX_M_BIAS); break;
+          case DX_M_RS: DX_TILE(DX_M_RS); break;
+          case DX_M_RS | DX_M_BIAS | DX_M_GELU: DX_TILE(DX_M_RS | DX_M_BIAS | DX_M_GELU); break;
+          case DX_M_RES | DX_M_ROWSQ: DX_TILE(DX_M_RES | DX_M_ROWSQ); break;
+          case DX_M_BIAS | DX_M_RES | DX_M_ROWSQ: DX_TILE(DX_M_BIAS | DX_M_RES | DX_M_ROWSQ); break;
+          case DX_M_GELUBWD: DX_TILE(DX_M_GELUBWD); break;
+          case DX_M_RES | DX_M_CX: DX_TILE(DX_M_RES | DX_M_CX); break;
+          default: DX_TILE(-1); break;
         }
-        cp_async_commit();
-        mbar_wait(tmem_full_bar + slot, use & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int sc = chalf; sc < nsc; sc += 2) {
-          const int nc = n0 + sc * 64;
-          if (sc != chalf) {
-            if (e.res) stage_load_async(bufR, e.res, e.ldr, m_base, nc, e.M, e.N, lane);
-            if (xsrc) stage_load_async(bufX, xsrc, xld, m_base, nc, e.M, e.N, lane);
-            cp_async_commit();
-          }
-          cp_async_wait<0>();
-          __syncwarp();
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            float v[32];
-            tmem_ld32(acc + (uint32_t)(sc * 64 + half * 32), v);  // warp-collective
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int piece = half * 4 + j;
-              const int ncol = nc + piece * 8;
-              float t[8], r[8], a[8], o2[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
-              if (e.res) stage_piece_get(bufR, lane, piece, r);
-              if (xsrc) stage_piece_get(bufX, lane, piece, a);
-              // aux and cx are mutually exclusive in every staged launch: `a` serves as both. N % 8 == 0 -> whole pieces.
-              if (row_ok && ncol < e.N) dx_epilogue_math<8>(e, rc, ncol, 8, t, r, a, a, o2, rs, rd);
-              stage_piece_put(bufR, lane, piece, t);
-              if (has_o2) stage_piece_put(bufO, lane, piece, o2);
-            }
-          }
-          __syncwarp();
-          if (e.out) stage_store(bufR, e.out, e.ldo, m_base, nc, e.M, e.N, lane);
-          if (has_o2) stage_store(bufO, e.out2, e.ldo2, m_base, nc, e.M, e.N, lane);
-          __syncwarp();
-        }
+#undef DX_TILE
       }
       // this warp has finished reading the accumulator: hand the TMEM slot back to the MMA issuer
       tc_fence_before();
@@ -477,11 +492,13 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   const bool pure_acc = d->accumulate && d->out_dtype == DX_F32 && !d->out2 && !d->res && !d->aux && !d->cx && !d->bias &&
                         !d->row_scale && !d->row_sumsq && !d->row_dot && d->act == DX_ACT_NONE;
   if (!STAGED && pure_acc && total < num_sms && num_kb >= 32) {
+    // smallest split whose work units fill >= 85 % of whole waves (atomic traffic grows with the split), else the best
     double best = (double)total / num_sms;
-    for (int sp = 2; sp <= 16 && num_kb / sp >= 16; ++sp) {
+    for (int sp = 2; sp <= 8 && num_kb / sp >= 32; ++sp) {
       const long long u = total * sp;
       const double eff = (double)u / ((double)((u + num_sms - 1) / num_sms) * num_sms);
       if (eff > best + 0.04) { best = eff; pp.splits = sp; }
+      if (eff >= 0.85) break;
     }
   }
   pp.kb_per_split = dx_ceil_div(num_kb, pp.splits);
@@ -518,8 +535,12 @@ int launch_staged(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& 
                   const DxEpi& e, cudaStream_t stream) {
   if (!d->a_mn && !d->b_mn) return launch_major<false, false, STAGED>(d, bn, stages, ta, tb, p, e, stream);
   if (!d->a_mn && d->b_mn) return launch_major<false, true, STAGED>(d, bn, stages, ta, tb, p, e, stream);
-  if (d->a_mn && !d->b_mn) return launch_major<true, false, STAGED>(d, bn, stages, ta, tb, p, e, stream);
-  return launch_major<true, true, STAGED>(d, bn, stages, ta, tb, p, e, stream);
+  if constexpr (!STAGED) {   // MN-major A only occurs in dW GEMMs (fp32 accumulate, direct epilogue): no staged instances
+    if (d->a_mn && !d->b_mn) return launch_major<true, false, STAGED>(d, bn, stages, ta, tb, p, e, stream);
+    return launch_major<true, true, STAGED>(d, bn, stages, ta, tb, p, e, stream);
+  }
+  dx_set_error("dx_gemm_tc: internal: staged epilogue with MN-major A");
+  return DX_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -540,7 +561,7 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
   const bool has_o2 = d->out2 != nullptr && (d->act == DX_ACT_GELU || d->act == DX_ACT_GELU_BWD);
   const bool any_side = d->out || d->res || d->aux || d->cx;
   const bool staged = any_side && e.vec_ok && d->act_dtype == DX_BF16 && (!d->out || d->out_dtype == DX_BF16) &&
-                      !d->accumulate && (d->N % 8 == 0) && !(d->aux && d->cx);
+                      !d->accumulate && (d->N % 8 == 0) && !(d->aux && d->cx) && !d->a_mn;
   // staging blocks per epilogue warp: res -> out (in place) [0], aux|cx [1], out2 [last]
   const int nbufs = staged ? (1 + ((d->aux || d->cx) ? 1 : 0) + (has_o2 ? 1 : 0)) : 0;
   const bool user_cfg = bn > 0;
@@ -573,6 +594,7 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
   p.b_lbo = b_lbo >= 0 ? b_lbo : (d->b_mn ? 8192 : 16);
   p.b_sbo = b_sbo >= 0 ? b_sbo : 1024;
   p.stage_bufs = nbufs;
+  p.epi_mask = staged ? dx_epi_mask(d) : -1;
   if (staged) return launch_staged<true>(d, bn, stages, ta, tb, p, e, stream);
   return launch_staged<false>(d, bn, stages, ta, tb, p, e, stream);
 }
