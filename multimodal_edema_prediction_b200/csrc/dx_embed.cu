@@ -157,31 +157,29 @@ __global__ void __launch_bounds__(NT) embed_special_kernel(EmbedIn in, const flo
   }
 }
 
-// grads of special_embeddings[0] (MASK), [1] ([REP]) and of the tab_encoder output; one block per sample.
+// grads of special_embeddings[0] (MASK), [1] ([REP]) and of the tab_encoder output; one block per (sample, time row).
 // Every special cell of dpsi is zeroed afterwards (the embedding MLP outputs there were overwritten in the forward).
 template <typename T>
 __global__ void __launch_bounds__(NT) embed_special_bwd_kernel(EmbedIn in, T* __restrict__ dpsi, float* __restrict__ dsp /*[8,d]*/,
-                                                              float* __restrict__ dtab /*[B,d]*/) {
+                                                              float* __restrict__ dtab /*[B,d], zeroed by the caller*/) {
   const int d = in.d, V = in.V, T_ = in.T;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / (T_ + 1), t = blockIdx.x % (T_ + 1);
   for (int dd = threadIdx.x; dd < d; dd += NT) {  // threads over dd: coalesced across the d-vector
     float a0 = 0.f, a1 = 0.f, at = 0.f;
-    for (int t = 0; t <= T_; ++t) {
-      for (int v = 0; v <= V; ++v) {
+    for (int v = 0; v <= V; ++v) {
+      const bool masked = cell_masked(in, b, t, v);
+      if (masked || t == T_ || v == V) {
         T* p = dpsi + ((((long long)b * (T_ + 1) + t) * (V + 1)) + v) * d + dd;
-        const bool masked = cell_masked(in, b, t, v);
-        if (masked || t == T_ || v == V) {
-          const float g = dx_ld(p);
-          if (masked) a0 += g;
-          else if (t == T_) a1 += g;
-          else at += g;
-          dx_st(p, 0.f);
-        }
+        const float g = dx_ld(p);
+        if (masked) a0 += g;
+        else if (t == T_) a1 += g;
+        else at += g;
+        dx_st(p, 0.f);
       }
     }
-    atomicAdd(dsp + dd, a0);
-    atomicAdd(dsp + d + dd, a1);
-    dtab[(long long)b * d + dd] = at;
+    if (a0 != 0.f) atomicAdd(dsp + dd, a0);
+    if (a1 != 0.f) atomicAdd(dsp + d + dd, a1);
+    if (at != 0.f) atomicAdd(dtab + (long long)b * d + dd, at);
   }
 }
 
@@ -337,8 +335,10 @@ int dx_embed_special_bwd(const float* xs, int B, int T, int V, int d, void* dpsi
   DX_CHECK_ARG(xs && dpsi && dspecial && dtab, "dx_embed_special_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   EmbedIn in{xs, B, T, V, d, nullptr, nullptr, nullptr};
-  if (act_dtype == DX_BF16) embed_special_bwd_kernel<bf16><<<B, NT, 0, st>>>(in, (bf16*)dpsi, dspecial, dtab);
-  else embed_special_bwd_kernel<float><<<B, NT, 0, st>>>(in, (float*)dpsi, dspecial, dtab);
+  DX_CUDA(cudaMemsetAsync(dtab, 0, sizeof(float) * (size_t)B * d, st));
+  const int nthr = d >= 256 ? 256 : (d >= 128 ? 128 : 64);
+  if (act_dtype == DX_BF16) embed_special_bwd_kernel<bf16><<<B * (T + 1), nthr, 0, st>>>(in, (bf16*)dpsi, dspecial, dtab);
+  else embed_special_bwd_kernel<float><<<B * (T + 1), nthr, 0, st>>>(in, (float*)dpsi, dspecial, dtab);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }

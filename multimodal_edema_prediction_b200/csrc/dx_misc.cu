@@ -88,7 +88,26 @@ __global__ void __launch_bounds__(NT) adamw_kernel(float* __restrict__ p, const 
     bc2 = 1.f - powf(b2, st);
   }
   if (lr_scale_dev) lr *= lr_scale_dev[0];
-  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+  const float inv_bc1 = 1.f / bc1, inv_sbc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
+  // main part: float4 (flat buffers are 32 B aligned slices); every stream is touched exactly once
+  const long long n4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 ? (n >> 2) : 0;
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n4; i += (long long)gridDim.x * NT) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    const float ge[4] = {g4.x * gs, g4.y * gs, g4.z * gs, g4.w * gs};
+    float pe[4] = {p4.x, p4.y, p4.z, p4.w}, me[4] = {m4.x, m4.y, m4.z, m4.w}, ve[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      me[j] = b1 * me[j] + (1.f - b1) * ge[j];
+      ve[j] = b2 * ve[j] + (1.f - b2) * ge[j] * ge[j];
+      pe[j] = pe[j] * decay - (lr * inv_bc1) * me[j] / (sqrtf(ve[j]) * inv_sbc2 + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(me[0], me[1], me[2], me[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
     const float gi = g[i] * gs;
     float pi = p[i];
     pi -= lr * wd * pi;  // decoupled weight decay (torch.optim.AdamW)

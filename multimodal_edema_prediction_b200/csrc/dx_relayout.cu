@@ -122,6 +122,31 @@ __global__ void __launch_bounds__(NT) colsum_kernel(const T* __restrict__ X, lon
   else atomicAdd(out + n, s);
 }
 
+// vector variant: each thread owns 8 adjacent columns (16 B bf16 / 32 B f32 loads; a warp reads 512 contiguous bytes per row)
+template <typename T>
+__global__ void __launch_bounds__(NT) colsum_vec_kernel(const T* __restrict__ X, long long ld, int M, long long N,
+                                                       float* __restrict__ out, int accumulate, int rows_per_block) {
+  const long long n = ((long long)blockIdx.x * NT + threadIdx.x) * 8;
+  if (n >= N) return;
+  const int m0 = blockIdx.y * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const T* p = X + (long long)m0 * ld + n;
+  for (int m = m0; m < m1; ++m, p += ld) {
+    float v[8];
+    dx_ld8(p, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+  if (gridDim.y == 1 && !accumulate) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[n + j] = acc[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(out + n + j, acc[j]);
+  }
+}
+
 // y (+)= alpha * x  over n elements (n % 8 == 0)
 template <typename T>
 __global__ void __launch_bounds__(NT) axpy_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec, float alpha,
@@ -198,7 +223,9 @@ int dx_relayout_bwd(const void* gdst, const void* src, const float* src_rowsq, c
 int dx_colsum(const void* X, int64_t ld, int M, int64_t N, float* out, int accumulate, int dtype, void* stream) {
   DX_CHECK_ARG(X && out && M > 0 && N > 0, "dx_colsum: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  const int gx = dx_ceil_div(N, NT);
+  const long long esz = dtype == DX_BF16 ? 2 : 4;
+  const bool vec = (N % 8 == 0) && ((uintptr_t)X % 16 == 0) && ((ld * esz) % 16 == 0);
+  const int gx = vec ? dx_ceil_div(N / 8, NT) : dx_ceil_div(N, NT);
   // enough row-splits to fill the machine when N is small
   int gy = 1;
   if (gx < 296) { const int a = dx_ceil_div(M, 64), b = dx_ceil_div(592, gx); gy = a < b ? a : b; }
@@ -206,7 +233,10 @@ int dx_colsum(const void* X, int64_t ld, int M, int64_t N, float* out, int accum
   gy = dx_ceil_div(M, rpb);
   if (gy > 1 && !accumulate) DX_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
   dim3 grid(gx, gy);
-  if (dtype == DX_BF16) colsum_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)X, ld, M, N, out, accumulate, rpb);
+  if (vec) {
+    if (dtype == DX_BF16) colsum_vec_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)X, ld, M, N, out, accumulate, rpb);
+    else colsum_vec_kernel<float><<<grid, NT, 0, st>>>((const float*)X, ld, M, N, out, accumulate, rpb);
+  } else if (dtype == DX_BF16) colsum_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)X, ld, M, N, out, accumulate, rpb);
   else colsum_kernel<float><<<grid, NT, 0, st>>>((const float*)X, ld, M, N, out, accumulate, rpb);
   DX_LAUNCH_CHECK();
   return DX_OK;
