@@ -79,13 +79,14 @@ def run_reference(args):
     Pl = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P.items()}
     xs, xt, tm, _ = O.feats_to_input(b["x_ts"], b["x_static"], b["bin_ends"], cfg.T)
 
+    cpu_opt = torch.optim.AdamW([v for v in Pl.values() if torch.is_tensor(v) and v.requires_grad], lr=1e-4, weight_decay=1e-5)
+
     def step():
-        for v in Pl.values():
-            if torch.is_tensor(v) and v.requires_grad:
-                v.grad = None
+        cpu_opt.zero_grad(set_to_none=True)
         z = O.model_forward_supervised(Pl, cfg, xs, xt, tm, "rep_token")
         loss = O.supervised_loss(z, b["y"], 0.3)
         loss.backward()
+        cpu_opt.step()
         return float(loss)
 
     for _ in range(args.warmup):
@@ -95,7 +96,7 @@ def run_reference(args):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     val = Bs / dt
-    sample = f"{Bs} of the {WORK['B']} samples of one step, fwd+loss+bwd, fp32, torch CPU"
+    sample = f"{Bs} of the {WORK['B']} samples of one step, fwd+loss+bwd+AdamW, fp32, torch CPU"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -342,9 +343,15 @@ def main():
             "allreduce_buckets_per_step": red.launched, "host_enqueue_ms_per_step": host_ms,
             "cuda_graph": gstep is not None, "cuda_graph_error": graph_err, "eager_ms_per_step": ms_eager / args.steps,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured step graph holds NCCL kernels of this communicator; tearing the communicator down underneath it
+        # (destroy_process_group / interpreter shutdown order) was seen to block forever on 2 GPUs.  Everything is
+        # measured and printed: drain the device, meet the other ranks, and leave without the collective teardown.
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

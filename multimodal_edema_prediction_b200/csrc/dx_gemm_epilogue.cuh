@@ -241,6 +241,8 @@ static inline int dx_epi_mask(const dx_gemm_desc* d) {
   else if (d->act == DX_ACT_GELU_BWD) { if (!d->out2 || !d->aux_bias || !d->row_scale2 || !d->row_dot) return -1; m |= DX_M_GELUBWD; }
   else if (d->act != DX_ACT_NONE) return -1;
   else if (d->aux || d->row_scale2 || d->row_dot) return -1;
+  // the specialised path stages bias / aux_bias through shared memory with 16 B cp.async
+  if ((d->bias && ((uintptr_t)d->bias & 15)) || (d->aux_bias && ((uintptr_t)d->aux_bias & 15)) || (d->bias_bs & 3)) return -1;
   switch (m) {
     case 0: case DX_M_BIAS: case DX_M_RS: case DX_M_RS | DX_M_BIAS | DX_M_GELU: case DX_M_RES | DX_M_ROWSQ:
     case DX_M_BIAS | DX_M_RES | DX_M_ROWSQ: case DX_M_GELUBWD: case DX_M_RES | DX_M_CX:
@@ -250,32 +252,28 @@ static inline int dx_epi_mask(const dx_gemm_desc* d) {
   }
 }
 
+// bv: the 8 per-column bias values of this piece (bias for BIAS, aux_bias for GELUBWD), staged by the caller.
 template <int MASK>
-__device__ __forceinline__ void dx_epilogue_math_c(const DxEpi& e, const DxRowConst& rc, int n0, float (&v)[8], const float (&r)[8],
-                                                   const float (&a)[8], float (&o2)[8], float& rs_acc, float& rd_acc) {
+__device__ __forceinline__ void dx_epilogue_math_c(const DxRowConst& rc, float (&v)[8], const float (&r)[8], const float (&a)[8],
+                                                   const float (&bv)[8], float (&o2)[8], float& rs_acc, float& rd_acc) {
   if constexpr ((MASK & DX_M_RS) != 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] *= rc.rs;
   }
   if constexpr ((MASK & DX_M_BIAS) != 0) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + n0));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += bv[i];
   }
   if constexpr ((MASK & DX_M_GELU) != 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { o2[i] = v[i]; v[i] = dx_gelu(v[i]); }
   }
   if constexpr ((MASK & DX_M_GELUBWD) != 0) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.aux_bias + n0));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.aux_bias + n0 + 4));
-    const float ab[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     float rd = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       v[i] *= dx_gelu_grad(a[i]);
-      rd = fmaf(v[i], a[i] - ab[i], rd);
+      rd = fmaf(v[i], a[i] - bv[i], rd);
       o2[i] = v[i];
       v[i] *= rc.rs2;
     }

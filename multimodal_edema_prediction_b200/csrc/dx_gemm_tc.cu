@@ -18,6 +18,7 @@
 //   direct  : thread-per-row 16 B vectors straight to global (fp32 outputs such as dW accumulation, unaligned shapes).
 #include "dx_gemm_epilogue.cuh"
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 namespace {
 
@@ -126,7 +127,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 struct TcParams {
   int K;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // descriptor byte offsets (test-overridable)
-  int stage_bufs;                        // staging blocks per epilogue warp (STAGED only), see stage layout below
+  int stage_bufs;                        // staging blocks per epilogue warp (STAGED only), see staged_epilogue
+  int stage_ring;                        // 1 or 2: ring depth of the res / aux|cx staging blocks (2 = prefetch one item ahead)
   int tiles_m, tiles_n, total_tiles;     // persistent work loop: unit -> (k split, batch z, m block, n block), n fastest
   int splits, kb_per_split;              // split-K (dW GEMMs with few output tiles): partial sums are red.add'ed into out
   int epi_mask;                          // staged epilogue: compile-time feature mask (dx_epi_mask), -1 = runtime flags
@@ -137,19 +139,24 @@ struct TcParams {
 // conflict-free both for the row-per-lane view (epilogue math) and for the 8-lanes-per-row view (global traffic).
 __device__ __forceinline__ uint32_t stg_off(int r, int p) { return (uint32_t)(r * 128 + ((p ^ (r & 7)) << 4)); }
 
-__device__ __forceinline__ void stage_store(const uint8_t* buf, void* base, long long ld, int m_base, int n0, int M, int N,
-                                            int lane) {
+__device__ __forceinline__ void stage_store(uint32_t buf, void* base, long long ld, int m_base, int n0, int M, int N, int lane) {
   const int piece = lane & 7, rsub = lane >> 3;
   const int col = n0 + piece * 8;
   if (col >= N) return;
   bf16* gp = reinterpret_cast<bf16*>(base) + (long long)(m_base + rsub) * ld + col;
   const long long gstep = 4 * ld;
-  const uint8_t* sp = buf + rsub * 128;
+  const uint32_t sp = buf + rsub * 128;
   const uint32_t pe = (uint32_t)((piece ^ rsub) << 4), po = (uint32_t)((piece ^ (rsub + 4)) << 4);
   const int rows = M - m_base - rsub;   // rows r = 4*i + rsub valid while 4*i < rows
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    if (4 * i < rows) *reinterpret_cast<uint4*>(gp + i * gstep) = *reinterpret_cast<const uint4*>(sp + i * 512 + ((i & 1) ? po : pe));
+    if (4 * i < rows) {
+      uint4 u;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                   : "r"(sp + i * 512 + ((i & 1) ? po : pe)));
+      *reinterpret_cast<uint4*>(gp + i * gstep) = u;
+    }
   }
 }
 // asynchronous variant of stage_load (cp.async 16 B, zero-fill out of range): prefetch of the next super-chunk
@@ -178,69 +185,170 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// One output tile of the staged epilogue for the calling epilogue warp.  MASK >= 0: compile-time feature set; -1: runtime.
-template <int BN, int MASK>
-__device__ __forceinline__ void staged_tile(const DxEpi& e, const DxRowConst& rc, uint32_t acc, uint8_t* wstg, int stage_bufs,
-                                            int m_base, bool row_ok, int n0, int chalf, int lane, uint64_t* full_bar,
-                                            uint32_t parity, float& rs, float& rd) {
-  constexpr bool CT = MASK >= 0;
-  const bool has_res = CT ? ((MASK & DX_M_RES) != 0) : (e.res != nullptr);
-  const bool has_x = CT ? ((MASK & (DX_M_CX | DX_M_GELUBWD)) != 0) : (e.aux != nullptr || e.cx != nullptr);
-  const bool has_o2 = CT ? ((MASK & (DX_M_GELU | DX_M_GELUBWD)) != 0) : dx_epi_has_out2(e);
-  const void* xsrc = e.aux ? e.aux : e.cx;
-  const long long xld = e.aux ? e.ldx : e.ldc;
-  uint8_t* bufR = wstg;
-  uint8_t* bufX = wstg + STG_BYTES;
-  uint8_t* bufO = wstg + (stage_bufs - 1) * STG_BYTES;
-  const int nsc = min(BN / 64, (e.N - n0 + 63) / 64);
-  // side tensors do not depend on the accumulator: start fetching them while the mainloop is still running
-  if (chalf < nsc) {
-    if (has_res) stage_load_async(bufR, e.res, e.ldr, m_base, n0 + chalf * 64, e.M, e.N, lane);
-    if (has_x) stage_load_async(bufX, xsrc, xld, m_base, n0 + chalf * 64, e.M, e.N, lane);
+// explicit shared-space 16 B accesses on staging blocks (generic pointers made ptxas emit LD.E/ST.E here)
+__device__ __forceinline__ void lds8(uint32_t addr, float (&v)[8]) {
+  uint4 u;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
   }
-  cp_async_commit();
-  mbar_wait(full_bar, parity);
-  tc_fence_after();
+}
+__device__ __forceinline__ void sts8(uint32_t addr, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+__device__ __forceinline__ void lds_f8(uint32_t addr, float (&v)[8]) {
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(addr + 16));
+}
+
+// The staged epilogue of one epilogue warp over ALL of its CTA's tiles.  MASK >= 0: compile-time feature set; -1: runtime.
+// The warp's work is a stream of items (tile, 64-column super-chunk).  Everything an item needs from global memory is
+// fetched with cp.async one item AHEAD (the first chunk of the NEXT tile included) while the current item is computed and
+// stored: always the 64 per-column bias values (a dependent LDG per 8-column piece showed up as 60 % long-scoreboard
+// stalls in ncu), and with p.stage_ring == 2 also the [32 x 64] blocks of the side tensors (res, aux|cx).
+// Staging blocks of a warp: R[ring] (res, reused in place for out), X[ring] (aux|cx, only if present), O (out2, if
+// present); wbias: 2 x 64 floats.
+template <int BN, int MASK>
+__device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams& p, uint32_t tmem_base, uint8_t* wstg,
+                                                uint8_t* wbias, int q, int chalf, int lane, uint64_t* tmem_full_bar,
+                                                uint64_t* tmem_empty_bar) {
+  constexpr bool CT = MASK >= 0;
+  const bool has_res = CT ? ((MASK & DX_M_RES) != 0) : (e0.res != nullptr);
+  const bool has_x = CT ? ((MASK & (DX_M_CX | DX_M_GELUBWD)) != 0) : (e0.aux != nullptr || e0.cx != nullptr);
+  const bool has_o2 = CT ? ((MASK & (DX_M_GELU | DX_M_GELUBWD)) != 0) : dx_epi_has_out2(e0);
+  constexpr bool has_b = CT && ((MASK & (DX_M_BIAS | DX_M_GELUBWD)) != 0);   // bias (or aux_bias) staged in wbias
+  const bool any_in = has_res || has_x;
+  const int ring = p.stage_ring;
+  const bool pf_side = any_in && ring == 2;
+  const uint32_t stg = smem_u32(wstg), sbias = smem_u32(wbias);
+  const uint32_t bufO = stg + (p.stage_bufs - 1) * STG_BYTES;
   const uint32_t lsw = (uint32_t)(lane & 7);
-  uint8_t* rowR = bufR + lane * 128;
-  const uint8_t* rowX = bufX + lane * 128;
-  uint8_t* rowO = bufO + lane * 128;
+  const int tiles_mn = p.tiles_n * p.tiles_m;
+  auto issue_side = [&](const DxEpi& e_, int b, int m_base_, int nc) {
+    if (has_res) stage_load_async(wstg + b * STG_BYTES, e_.res, e_.ldr, m_base_, nc, e_.M, e_.N, lane);
+    if (has_x) stage_load_async(wstg + (ring + b) * STG_BYTES, e_.aux ? e_.aux : e_.cx, e_.aux ? e_.ldx : e_.ldc, m_base_, nc, e_.M,
+                                e_.N, lane);
+  };
+  auto issue_bias = [&](const DxEpi& e_, int b, int nc) {   // 64 floats = 16 lanes x 16 B, zero-filled past N (N % 8 == 0)
+    if (lane < 16) {
+      const float* src = (MASK >= 0 && (MASK & DX_M_GELUBWD)) ? e_.aux_bias : e_.bias;
+      const int col = nc + lane * 4;
+      const bool ok = col < e_.N;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sbias + b * 256 + lane * 16), "l"(ok ? src + col : src),
+                   "r"(ok ? 16 : 0)
+                   : "memory");
+    }
+  };
+  int bi = 0, bb = 0;                         // ring slots of the current item (side blocks / bias)
+  bool side_loaded = false, bias_loaded = false;   // the current item's loads were issued while the previous item ran
+  uint32_t tcount = 0;
+  for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x, ++tcount) {
+    const int tile = unit / p.splits;
+    const int n0 = (tile % p.tiles_n) * BN;
+    const int m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
+    const int z = tile / tiles_mn;
+    const uint32_t slot = tcount & 1, use = tcount >> 1;
+    const uint32_t acc = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
+    DxEpi e = e0;
+    dx_epi_select_batch(e, z);
+    const int m_base = m0 + q * 32;
+    const int m = m_base + lane;
+    const bool row_ok = m < e.M;
+    const DxRowConst rc = row_ok ? dx_row_const(e, m) : DxRowConst{1.f, 1.f, 0.f};
+    float rs = 0.f, rd = 0.f;
+    const int nsc = min(BN / 64, (e.N - n0 + 63) / 64);
+    bool acc_ready = false;
 #pragma unroll 1
-  for (int sc = chalf; sc < nsc; sc += 2) {
-    const int nc = n0 + sc * 64;
-    if (sc != chalf) {
-      if (has_res) stage_load_async(bufR, e.res, e.ldr, m_base, nc, e.M, e.N, lane);
-      if (has_x) stage_load_async(bufX, xsrc, xld, m_base, nc, e.M, e.N, lane);
-      cp_async_commit();
-    }
-    cp_async_wait<0>();
-    __syncwarp();
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float v[32];
-      tmem_ld32(acc + (uint32_t)(sc * 64 + half * 32), v);  // warp-collective
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int piece = half * 4 + j;
-        const uint32_t po = ((uint32_t)piece ^ lsw) << 4;
-        const int ncol = nc + piece * 8;
-        float t[8], r[8], a[8], o2[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
-        if (has_res) dx_ld8(reinterpret_cast<const bf16*>(rowR + po), r);
-        if (has_x) dx_ld8(reinterpret_cast<const bf16*>(rowX + po), a);
-        if (row_ok && ncol < e.N) {   // N % 8 == 0 on this path: pieces are whole
-          if constexpr (CT) dx_epilogue_math_c<MASK>(e, rc, ncol, t, r, a, o2, rs, rd);
-          else dx_epilogue_math<8>(e, rc, ncol, 8, t, r, a, a, o2, rs, rd);   // aux and cx are mutually exclusive: `a` is both
-        }
-        dx_st8(reinterpret_cast<bf16*>(rowR + po), t);
-        if (has_o2) dx_st8(reinterpret_cast<bf16*>(rowO + po), o2);
+    for (int sc = chalf; sc < nsc; sc += 2) {
+      const int nc = n0 + sc * 64;
+      if ((any_in && !side_loaded) || (has_b && !bias_loaded)) {
+        if (any_in && !side_loaded) issue_side(e, bi, m_base, nc);
+        if (has_b && !bias_loaded) issue_bias(e, bb, nc);
+        cp_async_commit();
       }
+      // prefetch the next item of this warp's stream
+      bool next = false;
+      if (pf_side || has_b) {
+        int m_base2 = m_base, nc2 = nc + 128;
+        if (sc + 2 < nsc) {
+          next = true;
+        } else {
+          const int unit2 = unit + gridDim.x;
+          if (unit2 < p.total_tiles) {
+            const int tile2 = unit2 / p.splits;
+            nc2 = (tile2 % p.tiles_n) * BN + chalf * 64;
+            m_base2 = ((tile2 / p.tiles_n) % p.tiles_m) * BM + q * 32;
+            next = (tile2 / tiles_mn == z) && nc2 < e.N;   // same batch slice: the pointers of `e` are valid for it
+          }
+        }
+        if (next) {
+          if (pf_side) issue_side(e, bi ^ 1, m_base2, nc2);
+          if (has_b) issue_bias(e, bb ^ 1, nc2);
+          cp_async_commit();
+        }
+      }
+      if (!acc_ready) {   // side tensors do not depend on the accumulator: their loads run under the mainloop
+        mbar_wait(tmem_full_bar + slot, use & 1);
+        tc_fence_after();
+        acc_ready = true;
+      }
+      if (next) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      __syncwarp();
+      const uint32_t bufR = stg + bi * STG_BYTES;
+      const uint32_t rowR = bufR + lane * 128;
+      const uint32_t rowX = stg + (ring + bi) * STG_BYTES + lane * 128;
+      const uint32_t rowO = bufO + lane * 128;
+      const uint32_t biasS = sbias + bb * 256;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tmem_ld32(acc + (uint32_t)(sc * 64 + half * 32), v);  // warp-collective
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int piece = half * 4 + j;
+          const uint32_t po = ((uint32_t)piece ^ lsw) << 4;
+          const int ncol = nc + piece * 8;
+          float t[8], r[8], a[8], o2[8], bv[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
+          if (has_res) lds8(rowR + po, r);
+          if (has_x) lds8(rowX + po, a);
+          if (has_b) lds_f8(biasS + piece * 32, bv);
+          if (row_ok && ncol < e.N) {   // N % 8 == 0 on this path: pieces are whole
+            if constexpr (CT) dx_epilogue_math_c<MASK>(rc, t, r, a, bv, o2, rs, rd);
+            else dx_epilogue_math<8>(e, rc, ncol, 8, t, r, a, a, o2, rs, rd);   // aux and cx are mutually exclusive: `a` is both
+          }
+          sts8(rowR + po, t);
+          if (has_o2) sts8(rowO + po, o2);
+        }
+      }
+      __syncwarp();
+      if (e.out) stage_store(bufR, e.out, e.ldo, m_base, nc, e.M, e.N, lane);
+      if (has_o2) stage_store(bufO, e.out2, e.ldo2, m_base, nc, e.M, e.N, lane);
+      __syncwarp();
+      side_loaded = next && pf_side;
+      bias_loaded = next && has_b;
+      if (pf_side) bi ^= 1;
+      if (has_b) bb ^= 1;
     }
+    if (!acc_ready) {   // this warp owns no column block of a narrow tile: still take part in the accumulator hand-shake
+      mbar_wait(tmem_full_bar + slot, use & 1);
+      tc_fence_after();
+    }
+    // this warp has finished reading the accumulator: hand the TMEM slot back to the MMA issuer
+    tc_fence_before();
     __syncwarp();
-    if (e.out) stage_store(bufR, e.out, e.ldo, m_base, nc, e.M, e.N, lane);
-    if (has_o2) stage_store(bufO, e.out2, e.ldo2, m_base, nc, e.M, e.N, lane);
-    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+    if (row_ok) dx_epilogue_flush_row(e, m, rs, rd);
   }
 }
 
@@ -362,24 +470,37 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     // ===== epilogue: warp w reads TMEM lanes [32*(w%4), +32); column blocks alternate between the quadrant's 2 warps =====
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;   // 0 or 1
-    // staging blocks of this warp (STAGED): [0] = res -> out (in place), [1] = aux|cx, last = out2
-    uint8_t* wstg = stg_base + (warp - 2) * p.stage_bufs * STG_BYTES;
-    uint32_t tcount = 0;
-    for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x, ++tcount) {
-      const int tile = unit / p.splits;
-      const int n0 = (tile % p.tiles_n) * BN;
-      const int m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
-      const int z = tile / (p.tiles_n * p.tiles_m);
-      const uint32_t slot = tcount & 1, use = tcount >> 1;
-      const uint32_t acc = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
-      DxEpi e = e0;
-      dx_epi_select_batch(e, z);
-      const int m_base = m0 + q * 32;
-      const int m = m_base + lane;
-      const bool row_ok = m < e.M;
-      const DxRowConst rc = row_ok ? dx_row_const(e, m) : DxRowConst{1.f, 1.f, 0.f};
-      float rs = 0.f, rd = 0.f;
-      if (!STAGED) {
+    if constexpr (STAGED) {
+      uint8_t* wstg = stg_base + (warp - 2) * p.stage_bufs * STG_BYTES;
+      uint8_t* wbias = stg_base + NEPI * p.stage_bufs * STG_BYTES + (warp - 2) * 512;   // 2 x 64 floats
+#define DX_EPI(MASKV) staged_epilogue<BN, MASKV>(e0, p, tmem_base, wstg, wbias, q, chalf, lane, tmem_full_bar, tmem_empty_bar)
+      switch (p.epi_mask) {
+        case 0: DX_EPI(0); break;
+        case DX_M_BIAS: DX_EPI(DX_M_BIAS); break;
+        case DX_M_RS: DX_EPI(DX_M_RS); break;
+        case DX_M_RS | DX_M_BIAS | DX_M_GELU: DX_EPI(DX_M_RS | DX_M_BIAS | DX_M_GELU); break;
+        case DX_M_RES | DX_M_ROWSQ: DX_EPI(DX_M_RES | DX_M_ROWSQ); break;
+        case DX_M_BIAS | DX_M_RES | DX_M_ROWSQ: DX_EPI(DX_M_BIAS | DX_M_RES | DX_M_ROWSQ); break;
+        case DX_M_GELUBWD: DX_EPI(DX_M_GELUBWD); break;
+        case DX_M_RES | DX_M_CX: DX_EPI(DX_M_RES | DX_M_CX); break;
+        default: DX_EPI(-1); break;
+      }
+#undef DX_EPI
+    } else {
+      uint32_t tcount = 0;
+      for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x, ++tcount) {
+        const int tile = unit / p.splits;
+        const int n0 = (tile % p.tiles_n) * BN;
+        const int m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
+        const int z = tile / (p.tiles_n * p.tiles_m);
+        const uint32_t slot = tcount & 1, use = tcount >> 1;
+        const uint32_t acc = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
+        DxEpi e = e0;
+        dx_epi_select_batch(e, z);
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < e.M;
+        const DxRowConst rc = row_ok ? dx_row_const(e, m) : DxRowConst{1.f, 1.f, 0.f};
+        float rs = 0.f, rd = 0.f;
         mbar_wait(tmem_full_bar + slot, use & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -397,26 +518,12 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
             }
           }
         }
-      } else {
-#define DX_TILE(MASKV) staged_tile<BN, MASKV>(e, rc, acc, wstg, p.stage_bufs, m_base, row_ok, n0, chalf, lane, tmem_full_bar + slot, use & 1, rs, rd)
-        switch (p.epi_mask) {
-          case 0: DX_TILE(0); break;
-          case DX_M_BIAS: DX_TILE(DX_M_BIAS); break;
-          case DX_M_RS: DX_TILE(DX_M_RS); break;
-          case DX_M_RS | DX_M_BIAS | DX_M_GELU: DX_TILE(DX_M_RS | DX_M_BIAS | DX_M_GELU); break;
-          case DX_M_RES | DX_M_ROWSQ: DX_TILE(DX_M_RES | DX_M_ROWSQ); break;
-          case DX_M_BIAS | DX_M_RES | DX_M_ROWSQ: DX_TILE(DX_M_BIAS | DX_M_RES | DX_M_ROWSQ); break;
-          case DX_M_GELUBWD: DX_TILE(DX_M_GELUBWD); break;
-          case DX_M_RES | DX_M_CX: DX_TILE(DX_M_RES | DX_M_CX); break;
-          default: DX_TILE(-1); break;
-        }
-#undef DX_TILE
+        // this warp has finished reading the accumulator: hand the TMEM slot back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+        if (row_ok) dx_epilogue_flush_row(e, m, rs, rd);
       }
-      // this warp has finished reading the accumulator: hand the TMEM slot back to the MMA issuer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
-      if (row_ok) dx_epilogue_flush_row(e, m, rs, rd);
     }
   }
   tc_fence_before();
@@ -465,7 +572,7 @@ template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED>
 int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, const DxEpi& e,
                cudaStream_t stream) {
   const int smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/ +
-                   (STAGED ? NEPI * p.stage_bufs * STG_BYTES : 0);
+                   (STAGED ? NEPI * (p.stage_bufs * STG_BYTES + 512) : 0);
   if (smem > 232448) {
     dx_set_error("dx_gemm_tc: tile config BN=%d stages=%d needs %d B of shared memory", BN, STAGES, smem);
     return DX_ERR_UNSUPPORTED;
@@ -562,20 +669,34 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
   const bool any_side = d->out || d->res || d->aux || d->cx;
   const bool staged = any_side && e.vec_ok && d->act_dtype == DX_BF16 && (!d->out || d->out_dtype == DX_BF16) &&
                       !d->accumulate && (d->N % 8 == 0) && !(d->aux && d->cx) && !d->a_mn;
-  // staging blocks per epilogue warp: res -> out (in place) [0], aux|cx [1], out2 [last]
-  const int nbufs = staged ? (1 + ((d->aux || d->cx) ? 1 : 0) + (has_o2 ? 1 : 0)) : 0;
+  // staging blocks per epilogue warp: R[ring] (res -> out in place), X[ring] (aux|cx), O (out2).  Shallow-K GEMMs with [M,N]
+  // side inputs are HBM-bound on those inputs: they get the 2-deep ring (prefetch one item ahead); deep-K ones keep the
+  // shared memory for the operand ring.
+  const bool side_in = d->res || d->aux || d->cx;
+  int ring = (staged && side_in && d->K <= 1024) ? 2 : 1;
+  if (const char* env = getenv("DX_GEMM_STAGE_RING")) ring = (atoi(env) == 2 && staged && side_in) ? 2 : 1;
   const bool user_cfg = bn > 0;
-  if (!user_cfg) {
+  int nbufs = 0;
+  for (;; ring = 1) {
+    nbufs = staged ? (ring + ((d->aux || d->cx) ? ring : 0) + (has_o2 ? 1 : 0)) : 0;
+    const int budget = 232448 - 1280 - (staged ? NEPI * (nbufs * STG_BYTES + 512) : 0);
+    if (user_cfg) {
+      if (ring == 1 || stages * (BM + bn) * BK * 2 <= budget) break;
+      continue;
+    }
     // 128x256 tiles halve the L2 operand re-reads of 128x128 ones (every shape with N >= 256 uses them); narrow outputs get
     // 128x128 / 128x64.  The operand ring takes the deepest instantiated depth that fits next to the epilogue staging.
     bn = d->N <= 64 ? 64 : (d->N >= 256 ? 256 : 128);
-    const int budget = 232448 - 1280 - NEPI * nbufs * STG_BYTES;
     const int stage_bytes = (BM + bn) * BK * 2;
     const int cand[3][3] = {{4, 4, 4}, {6, 4, 3}, {4, 3, 2}};
     const int* c = cand[bn == 64 ? 0 : (bn == 128 ? 1 : 2)];
-    stages = c[2];
+    stages = 0;
     for (int i = 0; i < 3; ++i)
       if (c[i] * stage_bytes <= budget) { stages = c[i]; break; }
+    if (stages || ring == 1) {
+      if (!stages) stages = c[2];   // reported as unsupported by launch_cfg
+      break;
+    }
   }
   CUtensorMap ta, tb;
   if (!d->a_mn) rc = make_tmap(&ta, d->A, d->K, d->M, d->lda, batch, d->a_bs, BK, BM);
@@ -594,6 +715,7 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
   p.b_lbo = b_lbo >= 0 ? b_lbo : (d->b_mn ? 8192 : 16);
   p.b_sbo = b_sbo >= 0 ? b_sbo : 1024;
   p.stage_bufs = nbufs;
+  p.stage_ring = ring;
   p.epi_mask = staged ? dx_epi_mask(d) : -1;
   if (staged) return launch_staged<true>(d, bn, stages, ta, tb, p, e, stream);
   return launch_staged<false>(d, bn, stages, ta, tb, p, e, stream);

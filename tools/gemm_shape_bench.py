@@ -1,5 +1,5 @@
 """Times one dx_gemm shape/epilogue with CUDA events (and is the command profiled under ncu).
-usage: python tools/gemm_shape_bench.py M N K [epi] [iters]   epi in plain|dx|resid|ffn_in|gelu_bwd|dw"""
+usage: python tools/gemm_shape_bench.py M N K [epi] [iters]   epi in plain|bias|res_rowsq|dx|resid|ffn_in|gelu_bwd|dw"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -30,6 +30,11 @@ else:
     elif epi == "resid":
         kw.update(res=rn(M, N).to(bf), bias=rn(N), row_sumsq=torch.zeros(M, device="cuda"))
         nbytes += M * N * 2
+    elif epi == "res_rowsq":
+        kw.update(res=rn(M, N).to(bf), row_sumsq=torch.zeros(M, device="cuda"))
+        nbytes += M * N * 2
+    elif epi == "bias":
+        kw.update(bias=rn(N))
     elif epi == "ffn_in":
         kw.update(row_scale=torch.rand(M, device="cuda"), bias=rn(N), act=ops.ACT_GELU, out2=torch.empty(M, N, device="cuda", dtype=bf))
         nbytes += M * N * 2
