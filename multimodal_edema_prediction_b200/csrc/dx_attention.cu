@@ -9,8 +9,30 @@
 // backward: kernel A (per query) -> D = <do,o>, dq ; kernel B (per key) -> dk, dv, streaming query tiles.
 #include "dx_common.cuh"
 #include "../../include/duett_b200.h"
+#include <cstdlib>
+
+// bf16 tensor-core path for short self-attention (dx_attention_mma.cu)
+bool dx_attn_mma_supported(const void* const* ptrs, const long long* bs, const long long* rs, int n, int Sq, int Sk, int dh);
+int dx_attn_mma_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
+                    long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse, int B, int H, int Sq,
+                    int Sk, int dh, cudaStream_t st);
+int dx_attn_mma_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
+                    long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs, const void* go, long long go_bs,
+                    long long go_rs, void* dq, long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs,
+                    void* dv, long long dv_bs, long long dv_rs, const float* lse, int B, int H, int Sq, int Sk, int dh,
+                    cudaStream_t st);
 
 namespace {
+
+// DX_ATTN_SIMT=1 forces the SIMT kernels (A/B timing, debugging)
+bool attn_force_simt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DX_ATTN_SIMT");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
 
 constexpr int KT = 64;    // keys (or queries) per shared-memory tile
 constexpr int NTH = 128;  // threads per block
@@ -316,6 +338,12 @@ int dx_attn_fwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_
                 int dh, int dtype, void* stream) {
   DX_CHECK_ARG(q && k && v && o, "dx_attn_fwd: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DX_BF16 && !attn_force_simt()) {
+    const void* ptrs[4] = {q, k, v, o};
+    const long long bs[4] = {q_bs, k_bs, v_bs, o_bs}, rs[4] = {q_rs, k_rs, v_rs, o_rs};
+    if (dx_attn_mma_supported(ptrs, bs, rs, 4, Sq, Sk, dh))
+      return dx_attn_mma_fwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, B, H, Sq, Sk, dh, st);
+  }
   AttnView Q{q, q_bs, q_rs}, K{k, k_bs, k_rs}, V{v, v_bs, v_rs};
   AttnViewW O{o, o_bs, o_rs};
   const float scale = 1.f / sqrtf((float)dh);
@@ -331,6 +359,14 @@ int dx_attn_bwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_
                 int dtype, void* stream) {
   DX_CHECK_ARG(q && k && v && o && go && dq && dk && dv && lse && D_ws, "dx_attn_bwd: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DX_BF16 && !attn_force_simt()) {
+    const void* ptrs[8] = {q, k, v, o, go, dq, dk, dv};
+    const long long bs[8] = {q_bs, k_bs, v_bs, o_bs, go_bs, dq_bs, dk_bs, dv_bs};
+    const long long rs[8] = {q_rs, k_rs, v_rs, o_rs, go_rs, dq_rs, dk_rs, dv_rs};
+    if (dx_attn_mma_supported(ptrs, bs, rs, 8, Sq, Sk, dh))
+      return dx_attn_mma_bwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, go, go_bs, go_rs, dq, dq_bs, dq_rs, dk,
+                             dk_bs, dk_rs, dv, dv_bs, dv_rs, lse, B, H, Sq, Sk, dh, st);
+  }
   AttnView Q{q, q_bs, q_rs}, K{k, k_bs, k_rs}, V{v, v_bs, v_rs}, O{o, o_bs, o_rs}, GO{go, go_bs, go_rs};
   AttnViewW DQ{dq, dq_bs, dq_rs}, DK{dk, dk_bs, dk_rs}, DV{dv, dv_bs, dv_rs};
   const float scale = 1.f / sqrtf((float)dh);
