@@ -311,7 +311,12 @@ def main():
                          "gbs": v[2] / (v[3] * 1e-3) / 1e9} for s, v in by_shape.items()), key=lambda r: -r["ms_total"])
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
-            json.dump({"steps": args.steps, "ms_per_step": ms / args.steps, "gemm_ms_per_step": tot_ms / args.steps,
+            ffma = {}
+            for (t, s, f, b, a, z) in prof:
+                if t != "tc":
+                    d = ffma.setdefault(s, [0, 0.0])
+                    d[0] += 1; d[1] += a.elapsed_time(z)
+            json.dump({"ffma_by_shape": {k: {"launches": v[0], "ms_total": v[1]} for k, v in ffma.items()}, "steps": args.steps, "ms_per_step": ms / args.steps, "gemm_ms_per_step": tot_ms / args.steps,
                        "gemm_share_of_step": tot_ms / ms, "by_shape": table}, open(args.profile_out, "w"), indent=1)
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "kernel": "dx_gemm_tc_kernel (tcgen05, all launches)",

@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(NT) embed_bwd_front_kernel(EmbedIn in, const f
 }
 
 int chunking(int V, int R, int& rows_per_block) {
-  int nch = max(1, (6 * 148 + V - 1) / V);
+  // every thread walks its rows with dependent 2-4 B loads (latency bound): many short blocks (~32 per SM) hide it
+  int nch = max(1, (32 * 148 + V - 1) / V);
   nch = min(nch, max(1, R / 32));
   rows_per_block = (R + nch - 1) / nch;
   rows_per_block = ((rows_per_block + 7) / 8) * 8;

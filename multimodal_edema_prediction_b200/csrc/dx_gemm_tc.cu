@@ -214,8 +214,8 @@ __device__ __forceinline__ void lds_f8(uint32_t addr, float (&v)[8]) {
 // fetched with cp.async one item AHEAD (the first chunk of the NEXT tile included) while the current item is computed and
 // stored: always the 64 per-column bias values (a dependent LDG per 8-column piece showed up as 60 % long-scoreboard
 // stalls in ncu), and with p.stage_ring == 2 also the [32 x 64] blocks of the side tensors (res, aux|cx).
-// Staging blocks of a warp: R[ring] (res, reused in place for out), X[ring] (aux|cx, only if present), O (out2, if
-// present); wbias: 2 x 64 floats.
+// Staging blocks of a warp: R[ring] (res, reused in place for out), X[ring] (aux|cx, only if present; reused in place for
+// out2), O (out2 when there is no X block); wbias: 2 x 64 floats.
 template <int BN, int MASK>
 __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams& p, uint32_t tmem_base, uint8_t* wstg,
                                                 uint8_t* wbias, int q, int chalf, int lane, uint64_t* tmem_full_bar,
@@ -229,7 +229,7 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
   const int ring = p.stage_ring;
   const bool pf_side = any_in && ring == 2;
   const uint32_t stg = smem_u32(wstg), sbias = smem_u32(wbias);
-  const uint32_t bufO = stg + (p.stage_bufs - 1) * STG_BYTES;
+  const uint32_t bufO_own = stg + (p.stage_bufs - 1) * STG_BYTES;   // used when there is no aux|cx block to reuse
   const uint32_t lsw = (uint32_t)(lane & 7);
   const int tiles_mn = p.tiles_n * p.tiles_m;
   auto issue_side = [&](const DxEpi& e_, int b, int m_base_, int nc) {
@@ -306,6 +306,8 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
       const uint32_t bufR = stg + bi * STG_BYTES;
       const uint32_t rowR = bufR + lane * 128;
       const uint32_t rowX = stg + (ring + bi) * STG_BYTES + lane * 128;
+      // out2 is staged in place over the aux block when there is one (each lane rewrites the 16 B piece it has just read)
+      const uint32_t bufO = has_x ? stg + (ring + bi) * STG_BYTES : bufO_own;
       const uint32_t rowO = bufO + lane * 128;
       const uint32_t biasS = sbias + bb * 256;
 #pragma unroll
@@ -678,7 +680,7 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
   const bool user_cfg = bn > 0;
   int nbufs = 0;
   for (;; ring = 1) {
-    nbufs = staged ? (ring + ((d->aux || d->cx) ? ring : 0) + (has_o2 ? 1 : 0)) : 0;
+    nbufs = staged ? (ring + ((d->aux || d->cx) ? ring : (has_o2 ? 1 : 0))) : 0;
     const int budget = 232448 - 1280 - (staged ? NEPI * (nbufs * STG_BYTES + 512) : 0);
     if (user_cfg) {
       if (ring == 1 || stages * (BM + bn) * BK * 2 <= budget) break;

@@ -81,7 +81,10 @@ class LinearFn(torch.autograd.Function):
             gx = gx2.reshape(*ctx.lead, K)
         if ctx.needs_input_grad[1]:
             sink, gw = grad_sink(weight)
-            ops.gemm_(g2, x2, a_mn=True, b_mn=True, out=sink, accumulate=True)  # dW += dY^T @ X
+            split, rows = 0, g2.shape[0]
+            if x2.dtype == torch.float32 and rows >= 2048 and ((N + 63) // 64) * ((K + 127) // 128) <= 32:
+                split = min(64, rows // 256)   # few output tiles, long reduction over rows (e.g. Linear(1, 128) over B*T rows)
+            ops.gemm_(g2, x2, a_mn=True, b_mn=True, out=sink, accumulate=True, split_k=split)  # dW += dY^T @ X
         if ctx.has_bias and ctx.needs_input_grad[2]:
             sink, gb = grad_sink(bias)
             ops.colsum(g2, sink, accumulate=True)
