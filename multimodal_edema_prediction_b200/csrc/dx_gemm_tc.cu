@@ -178,6 +178,7 @@ __device__ __forceinline__ void stage_load_async(uint8_t* buf, const void* base,
                  : "memory");
   }
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -217,9 +218,9 @@ __device__ __forceinline__ void lds_f8(uint32_t addr, float (&v)[8]) {
 // Staging blocks of a warp: R[ring] (res, reused in place for out), X[ring] (aux|cx, only if present; reused in place for
 // out2), O (out2 when there is no X block); wbias: 2 x 64 floats.
 template <int BN, int MASK>
-__device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams& p, uint32_t tmem_base, uint8_t* wstg,
-                                                uint8_t* wbias, int q, int chalf, int lane, uint64_t* tmem_full_bar,
-                                                uint64_t* tmem_empty_bar) {
+__device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams& p, const CUtensorMap* tmR, const CUtensorMap* tmX,
+                                                uint32_t tmem_base, uint8_t* wstg, uint8_t* wbias, uint64_t* sfull, int q,
+                                                int chalf, int lane, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
   constexpr bool CT = MASK >= 0;
   const bool has_res = CT ? ((MASK & DX_M_RES) != 0) : (e0.res != nullptr);
   const bool has_x = CT ? ((MASK & (DX_M_CX | DX_M_GELUBWD)) != 0) : (e0.aux != nullptr || e0.cx != nullptr);
@@ -232,11 +233,16 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
   const uint32_t bufO_own = stg + (p.stage_bufs - 1) * STG_BYTES;   // used when there is no aux|cx block to reuse
   const uint32_t lsw = (uint32_t)(lane & 7);
   const int tiles_mn = p.tiles_n * p.tiles_m;
-  auto issue_side = [&](const DxEpi& e_, int b, int m_base_, int nc) {
-    if (has_res) stage_load_async(wstg + b * STG_BYTES, e_.res, e_.ldr, m_base_, nc, e_.M, e_.N, lane);
-    if (has_x) stage_load_async(wstg + (ring + b) * STG_BYTES, e_.aux ? e_.aux : e_.cx, e_.aux ? e_.ldx : e_.ldc, m_base_, nc, e_.M,
-                                e_.N, lane);
+  // [32 x 64] blocks of res / aux|cx: one TMA box each (128B swizzle = the staging layout), completion on sfull[b].  The
+  // bulk-async path keeps whole blocks in flight without occupying L1 miss slots the way 16 B cp.async requests did.
+  auto issue_side = [&](int b, int m_base_, int nc, int z_) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(sfull + b, (uint32_t)((has_res ? STG_BYTES : 0) + (has_x ? STG_BYTES : 0)));
+      if (has_res) tma_load_3d(wstg + b * STG_BYTES, tmR, sfull + b, nc, m_base_, z_);
+      if (has_x) tma_load_3d(wstg + (ring + b) * STG_BYTES, tmX, sfull + b, nc, m_base_, z_);
+    }
   };
+  uint32_t sphase = 0;   // bit b: parity of the next completion of sfull[b]
   auto issue_bias = [&](const DxEpi& e_, int b, int nc) {   // 64 floats = 16 lanes x 16 B, zero-filled past N (N % 8 == 0)
     if (lane < 16) {
       const float* src = (MASK >= 0 && (MASK & DX_M_GELUBWD)) ? e_.aux_bias : e_.bias;
@@ -269,9 +275,9 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
 #pragma unroll 1
     for (int sc = chalf; sc < nsc; sc += 2) {
       const int nc = n0 + sc * 64;
-      if ((any_in && !side_loaded) || (has_b && !bias_loaded)) {
-        if (any_in && !side_loaded) issue_side(e, bi, m_base, nc);
-        if (has_b && !bias_loaded) issue_bias(e, bb, nc);
+      if (any_in && !side_loaded) issue_side(bi, m_base, nc, z);
+      if (has_b && !bias_loaded) {
+        issue_bias(e, bb, nc);
         cp_async_commit();
       }
       // prefetch the next item of this warp's stream
@@ -290,9 +296,11 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
           }
         }
         if (next) {
-          if (pf_side) issue_side(e, bi ^ 1, m_base2, nc2);
-          if (has_b) issue_bias(e, bb ^ 1, nc2);
-          cp_async_commit();
+          if (pf_side) issue_side(bi ^ 1, m_base2, nc2, z);
+          if (has_b) {
+            issue_bias(e, bb ^ 1, nc2);
+            cp_async_commit();
+          }
         }
       }
       if (!acc_ready) {   // side tensors do not depend on the accumulator: their loads run under the mainloop
@@ -300,8 +308,14 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
         tc_fence_after();
         acc_ready = true;
       }
-      if (next) cp_async_wait<1>();
-      else cp_async_wait<0>();
+      if (has_b) {
+        if (next) cp_async_wait<1>();
+        else cp_async_wait<0>();
+      }
+      if (any_in) {
+        mbar_wait(sfull + bi, (sphase >> bi) & 1u);
+        sphase ^= 1u << bi;
+      }
       __syncwarp();
       const uint32_t bufR = stg + bi * STG_BYTES;
       const uint32_t rowR = bufR + lane * 128;
@@ -336,6 +350,7 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
       __syncwarp();
       if (e.out) stage_store(bufR, e.out, e.ldo, m_base, nc, e.M, e.N, lane);
       if (has_o2) stage_store(bufO, e.out2, e.ldo2, m_base, nc, e.M, e.N, lane);
+      if (any_in) fence_proxy_async();   // generic-proxy accesses of these blocks are ordered before the next TMA write into them
       __syncwarp();
       side_loaded = next && pf_side;
       bias_loaded = next && has_b;
@@ -357,22 +372,28 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
 // ------------------------------------------------------------------------------------------------
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED>
 __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB, TcParams p,
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ CUtensorMap tmR,
+                                                             const __grid_constant__ CUtensorMap tmX, TcParams p,
                                                              DxEpi e0) {
   // Persistent CTA: loops over output tiles; the TMA producer and the MMA issuer run ahead of the epilogue warps
   // through a STAGES-deep operand ring and a 2-deep ring of TMEM accumulators (2*BN columns).
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
+  constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // allocation must be a power of two
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024 B alignment is required by the 128B swizzle atoms; align manually as well.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  // layout: operand ring | staging blocks (1024 B aligned: TMA 128B-swizzle destinations) | bias blocks | barriers
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
+  uint8_t* bias_base = stg_base + (STAGED ? NEPI * p.stage_bufs * STG_BYTES : 0);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_base + (STAGED ? NEPI * 512 : 0));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  uint8_t* stg_base = smem + STAGES * STAGE_BYTES + 256;
+  uint64_t* side_full_bar = tmem_empty_bar + 2;   // [NEPI][2]: side-tensor blocks of each epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(side_full_bar + 2 * NEPI);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -388,10 +409,11 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
       mbar_init(tmem_full_bar + s, 1);
       mbar_init(tmem_empty_bar + s, NEPI);   // one arrival per epilogue warp
     }
+    for (int s = 0; s < 2 * NEPI; ++s) mbar_init(side_full_bar + s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -474,8 +496,14 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     const int chalf = (warp - 2) >> 2;   // 0 or 1
     if constexpr (STAGED) {
       uint8_t* wstg = stg_base + (warp - 2) * p.stage_bufs * STG_BYTES;
-      uint8_t* wbias = stg_base + NEPI * p.stage_bufs * STG_BYTES + (warp - 2) * 512;   // 2 x 64 floats
-#define DX_EPI(MASKV) staged_epilogue<BN, MASKV>(e0, p, tmem_base, wstg, wbias, q, chalf, lane, tmem_full_bar, tmem_empty_bar)
+      uint8_t* wbias = bias_base + (warp - 2) * 512;   // 2 x 64 floats
+      uint64_t* sfull = side_full_bar + (warp - 2) * 2;
+      if (lane == 0) {
+        prefetch_tmap(&tmR);
+        prefetch_tmap(&tmX);
+      }
+#define DX_EPI(MASKV) \
+  staged_epilogue<BN, MASKV>(e0, p, &tmR, &tmX, tmem_base, wstg, wbias, sfull, q, chalf, lane, tmem_full_bar, tmem_empty_bar)
       switch (p.epi_mask) {
         case 0: DX_EPI(0); break;
         case DX_M_BIAS: DX_EPI(DX_M_BIAS); break;
@@ -530,7 +558,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -571,9 +599,9 @@ int make_tmap(CUtensorMap* map, const void* base, long long inner, long long out
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED>
-int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p, const DxEpi& e,
-               cudaStream_t stream) {
-  const int smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/ +
+int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr,
+               const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
+  const int smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 512 /*barriers*/ +
                    (STAGED ? NEPI * (p.stage_bufs * STG_BYTES + 512) : 0);
   if (smem > 232448) {
     dx_set_error("dx_gemm_tc: tile config BN=%d stages=%d needs %d B of shared memory", BN, STAGES, smem);
@@ -600,9 +628,10 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   const int num_kb = dx_ceil_div(d->K, BK);
   const bool pure_acc = d->accumulate && d->out_dtype == DX_F32 && !d->out2 && !d->res && !d->aux && !d->cx && !d->bias &&
                         !d->row_scale && !d->row_sumsq && !d->row_dot && d->act == DX_ACT_NONE;
-  if (!STAGED && pure_acc && total < num_sms && num_kb >= 32) {
+  const double eff1 = (double)total / ((double)((total + num_sms - 1) / num_sms) * num_sms);   // wave efficiency unsplit
+  if (!STAGED && pure_acc && eff1 < 0.85 && num_kb >= 64) {
     // smallest split whose work units fill >= 85 % of whole waves (atomic traffic grows with the split), else the best
-    double best = (double)total / num_sms;
+    double best = eff1;
     for (int sp = 2; sp <= 8 && num_kb / sp >= 32; ++sp) {
       const long long u = total * sp;
       const double eff = (double)u / ((double)((u + num_sms - 1) / num_sms) * num_sms);
@@ -620,33 +649,35 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   pp.total_tiles = (int)total;
   const int ctas_per_sm = smem <= 113 * 1024 ? 2 : 1;   // persistent grid: fill every SM, no more
   const int grid = (int)(total < (long long)num_sms * ctas_per_sm ? total : (long long)num_sms * ctas_per_sm);
-  kern<<<grid, NTHREADS, smem, stream>>>(ta, tb, pp, e);
+  kern<<<grid, NTHREADS, smem, stream>>>(ta, tb, tr, tx, pp, e);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }
 
 template <bool A_MN, bool B_MN, bool STAGED>
 int launch_major(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& ta, const CUtensorMap& tb,
-                 const TcParams& p, const DxEpi& e, cudaStream_t stream) {
-  if (bn == 256 && stages == 4) return launch_cfg<256, 4, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
-  if (bn == 256 && stages == 3) return launch_cfg<256, 3, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
-  if (bn == 256 && stages == 2) return launch_cfg<256, 2, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
-  if (bn == 128 && stages == 3) return launch_cfg<128, 3, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
-  if (bn == 128 && stages == 4) return launch_cfg<128, 4, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
-  if (bn == 128 && stages == 6) return launch_cfg<128, 6, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
-  if (bn == 64 && stages == 4) return launch_cfg<64, 4, A_MN, B_MN, STAGED>(d, ta, tb, p, e, stream);
+                 const CUtensorMap& tr, const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
+  if (bn == 256 && stages == 4) return launch_cfg<256, 4, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
+  if (bn == 256 && stages == 3) return launch_cfg<256, 3, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
+  if (bn == 256 && stages == 2) return launch_cfg<256, 2, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
+  if (bn == 192 && stages == 4) return launch_cfg<192, 4, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
+  if (bn == 192 && stages == 3) return launch_cfg<192, 3, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
+  if (bn == 128 && stages == 3) return launch_cfg<128, 3, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
+  if (bn == 128 && stages == 4) return launch_cfg<128, 4, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
+  if (bn == 128 && stages == 6) return launch_cfg<128, 6, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
+  if (bn == 64 && stages == 4) return launch_cfg<64, 4, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
   dx_set_error("dx_gemm_tc: unsupported tile config BN=%d stages=%d", bn, stages);
   return DX_ERR_UNSUPPORTED;
 }
 
 template <bool STAGED>
-int launch_staged(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p,
-                  const DxEpi& e, cudaStream_t stream) {
-  if (!d->a_mn && !d->b_mn) return launch_major<false, false, STAGED>(d, bn, stages, ta, tb, p, e, stream);
-  if (!d->a_mn && d->b_mn) return launch_major<false, true, STAGED>(d, bn, stages, ta, tb, p, e, stream);
+int launch_staged(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr,
+                  const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
+  if (!d->a_mn && !d->b_mn) return launch_major<false, false, STAGED>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
+  if (!d->a_mn && d->b_mn) return launch_major<false, true, STAGED>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
   if constexpr (!STAGED) {   // MN-major A only occurs in dW GEMMs (fp32 accumulate, direct epilogue): no staged instances
-    if (d->a_mn && !d->b_mn) return launch_major<true, false, STAGED>(d, bn, stages, ta, tb, p, e, stream);
-    return launch_major<true, true, STAGED>(d, bn, stages, ta, tb, p, e, stream);
+    if (d->a_mn && !d->b_mn) return launch_major<true, false, STAGED>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
+    return launch_major<true, true, STAGED>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
   }
   dx_set_error("dx_gemm_tc: internal: staged epilogue with MN-major A");
   return DX_ERR_UNSUPPORTED;
@@ -681,7 +712,7 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
   int nbufs = 0;
   for (;; ring = 1) {
     nbufs = staged ? (ring + ((d->aux || d->cx) ? ring : (has_o2 ? 1 : 0))) : 0;
-    const int budget = 232448 - 1280 - (staged ? NEPI * (nbufs * STG_BYTES + 512) : 0);
+    const int budget = 232448 - 1536 - (staged ? NEPI * (nbufs * STG_BYTES + 512) : 0);
     if (user_cfg) {
       if (ring == 1 || stages * (BM + bn) * BK * 2 <= budget) break;
       continue;
@@ -689,9 +720,11 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
     // 128x256 tiles halve the L2 operand re-reads of 128x128 ones (every shape with N >= 256 uses them); narrow outputs get
     // 128x128 / 128x64.  The operand ring takes the deepest instantiated depth that fits next to the epilogue staging.
     bn = d->N <= 64 ? 64 : (d->N >= 256 ? 256 : 128);
+    // narrow outputs whose last 256-column tile would be half empty (N = 384: QKV with 2 heads of 64) use 128x192 tiles
+    if (d->N > 128 && d->N < 1024 && (d->N % 256) > 128 && (d->N % 256) <= 192 && (d->N % 192) == 0) bn = 192;
     const int stage_bytes = (BM + bn) * BK * 2;
-    const int cand[3][3] = {{4, 4, 4}, {6, 4, 3}, {4, 3, 2}};
-    const int* c = cand[bn == 64 ? 0 : (bn == 128 ? 1 : 2)];
+    const int cand[4][3] = {{4, 4, 4}, {6, 4, 3}, {4, 3, 2}, {4, 3, 3}};
+    const int* c = cand[bn == 64 ? 0 : (bn == 128 ? 1 : (bn == 256 ? 2 : 3))];
     stages = 0;
     for (int i = 0; i < 3; ++i)
       if (c[i] * stage_bytes <= budget) { stages = c[i]; break; }
@@ -719,6 +752,17 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
   p.stage_bufs = nbufs;
   p.stage_ring = ring;
   p.epi_mask = staged ? dx_epi_mask(d) : -1;
-  if (staged) return launch_staged<true>(d, bn, stages, ta, tb, p, e, stream);
-  return launch_staged<false>(d, bn, stages, ta, tb, p, e, stream);
+  // side tensors of the staged epilogue: [32 rows x 64 columns] boxes of the [M,N] matrices (batch = third dimension)
+  CUtensorMap tr = ta, tx = ta;
+  if (staged && d->res) {
+    rc = make_tmap(&tr, d->res, d->N, d->M, d->ldr, batch, d->res_bs, 64, 32);
+    if (rc) return rc;
+  }
+  if (staged && (d->aux || d->cx)) {
+    rc = d->aux ? make_tmap(&tx, d->aux, d->N, d->M, d->ldx, batch, d->aux_bs, 64, 32)
+                : make_tmap(&tx, d->cx, d->N, d->M, d->ldc, batch, d->cx_bs, 64, 32);
+    if (rc) return rc;
+  }
+  if (staged) return launch_staged<true>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
+  return launch_staged<false>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
 }
