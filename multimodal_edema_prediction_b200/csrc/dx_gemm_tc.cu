@@ -95,6 +95,57 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: two SMs of a cluster share one 256 x BN tile -----------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into this CTA's shared memory whose bytes are counted on the LEADER CTA's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -217,7 +268,7 @@ __device__ __forceinline__ void lds_f8(uint32_t addr, float (&v)[8]) {
 // stalls in ncu), and with p.stage_ring == 2 also the [32 x 64] blocks of the side tensors (res, aux|cx).
 // Staging blocks of a warp: R[ring] (res, reused in place for out), X[ring] (aux|cx, only if present; reused in place for
 // out2), O (out2 when there is no X block); wbias: 2 x 64 floats.
-template <int BN, int MASK>
+template <int BN, int MASK, int CTAS>
 __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams& p, const CUtensorMap* tmR, const CUtensorMap* tmX,
                                                 uint32_t tmem_base, uint8_t* wstg, uint8_t* wbias, uint64_t* sfull, int q,
                                                 int chalf, int lane, uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar) {
@@ -256,10 +307,14 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
   int bi = 0, bb = 0;                         // ring slots of the current item (side blocks / bias)
   bool side_loaded = false, bias_loaded = false;   // the current item's loads were issued while the previous item ran
   uint32_t tcount = 0;
-  for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x, ++tcount) {
+  // CTA pair: both CTAs walk the same 256-row tiles; this CTA owns rows [rank*128, +128) of each
+  const int m_off = CTAS == 2 ? (int)cluster_ctarank() * BM : 0;
+  const int ustep = (int)gridDim.x / CTAS;
+  const uint32_t empty_remote = CTAS == 2 ? mapa_u32(smem_u32(tmem_empty_bar), 0) : 0;   // the leader's tmem_empty_bar[0]
+  for (int unit = (int)blockIdx.x / CTAS; unit < p.total_tiles; unit += ustep, ++tcount) {
     const int tile = unit / p.splits;
     const int n0 = (tile % p.tiles_n) * BN;
-    const int m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
+    const int m0 = ((tile / p.tiles_n) % p.tiles_m) * (BM * CTAS) + m_off;
     const int z = tile / tiles_mn;
     const uint32_t slot = tcount & 1, use = tcount >> 1;
     const uint32_t acc = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
@@ -287,11 +342,11 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
         if (sc + 2 < nsc) {
           next = true;
         } else {
-          const int unit2 = unit + gridDim.x;
+          const int unit2 = unit + ustep;
           if (unit2 < p.total_tiles) {
             const int tile2 = unit2 / p.splits;
             nc2 = (tile2 % p.tiles_n) * BN + chalf * 64;
-            m_base2 = ((tile2 / p.tiles_n) % p.tiles_m) * BM + q * 32;
+            m_base2 = ((tile2 / p.tiles_n) % p.tiles_m) * (BM * CTAS) + m_off + q * 32;
             next = (tile2 / tiles_mn == z) && nc2 < e.N;   // same batch slice: the pointers of `e` are valid for it
           }
         }
@@ -364,13 +419,16 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
     // this warp has finished reading the accumulator: hand the TMEM slot back to the MMA issuer
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+    if (lane == 0) {
+      if (CTAS == 2) mbar_arrive_cluster(empty_remote + slot * 8);
+      else mbar_arrive(tmem_empty_bar + slot);
+    }
     if (row_ok) dx_epilogue_flush_row(e, m, rs, rd);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED, int CTAS>
 __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmR,
@@ -378,8 +436,13 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
                                                              DxEpi e0) {
   // Persistent CTA: loops over output tiles; the TMA producer and the MMA issuer run ahead of the epilogue warps
   // through a STAGES-deep operand ring and a 2-deep ring of TMEM accumulators (2*BN columns).
+  // CTAS == 2: a cluster of two CTAs (one SM pair) computes a 256 x BN tile with tcgen05.mma.cta_group::2 issued by the
+  // leader (cluster rank 0).  Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), so the L2 -> SM
+  // operand traffic per FLOP drops by a third against 128 x BN single-CTA tiles; each CTA's TMEM holds its 128 accumulator
+  // rows and its own epilogue warps drain them.
+  constexpr int BNL = BN / CTAS;   // B rows staged by this CTA
   constexpr int A_BYTES = BM * BK * 2;
-  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int B_BYTES = BNL * BK * 2;
   constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // allocation must be a power of two
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -397,6 +460,8 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0;
+  const int unit0 = (int)blockIdx.x / CTAS, ustep = (int)gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -407,17 +472,23 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full_bar + s, 1);
-      mbar_init(tmem_empty_bar + s, NEPI);   // one arrival per epilogue warp
+      mbar_init(tmem_empty_bar + s, NEPI * CTAS);   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     for (int s = 0; s < 2 * NEPI; ++s) mbar_init(side_full_bar + s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (CTAS == 2) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything is signalled remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -425,10 +496,11 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       // ===== TMA producer =====
       uint32_t it = 0;   // running k-block counter across tiles
-      for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x) {
+      const uint32_t leader_full = CTAS == 2 ? mapa_u32(smem_u32(full_bar), 0) : 0;
+      for (int unit = unit0; unit < p.total_tiles; unit += ustep) {
         const int tile = unit / p.splits, split = unit - tile * p.splits;
-        const int n0 = (tile % p.tiles_n) * BN;
-        const int m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
+        const int n0 = (tile % p.tiles_n) * BN + (int)cta_rank * BNL;
+        const int m0 = ((tile / p.tiles_n) % p.tiles_m) * (BM * CTAS) + (int)cta_rank * BM;
         const int z = tile / (p.tiles_n * p.tiles_m);
         const int kb_lo = split * p.kb_per_split, kb_hi = min(num_kb, kb_lo + p.kb_per_split);
         for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
@@ -437,32 +509,50 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
           mbar_wait(empty_bar + s, ph ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
           const int k0 = kb * BK;
-          if (!A_MN) {
-            tma_load_3d(sa, &tmA, full_bar + s, k0, m0, z);  // box {64 k, 128 m, 1}
-          } else {
+          if (CTAS == 2) {
+            // both CTAs' bytes are counted on the leader's barrier (its MMA thread consumes both halves)
+            if (cta_rank == 0) mbar_arrive_expect_tx(full_bar + s, 2 * STAGE_BYTES);
+            const uint32_t lb = leader_full + s * 8;
+            if (!A_MN) {
+              tma_load_3d_pair(sa, &tmA, lb, k0, m0, z);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_3d(sa + c * 8192, &tmA, full_bar + s, m0 + c * 64, k0, z);  // {64 m, 64 k, 1}
-          }
-          if (!B_MN) {
-            tma_load_3d(sb, &tmB, full_bar + s, k0, n0, z);  // box {64 k, BN n, 1}
-          } else {
+              for (int c = 0; c < BM / 64; ++c) tma_load_3d_pair(sa + c * 8192, &tmA, lb, m0 + c * 64, k0, z);
+            }
+            if (!B_MN) {
+              tma_load_3d_pair(sb, &tmB, lb, k0, n0, z);  // box {64 k, BN/2 n, 1}
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_3d(sb + c * 8192, &tmB, full_bar + s, n0 + c * 64, k0, z);
+              for (int c = 0; c < BNL / 64; ++c) tma_load_3d_pair(sb + c * 8192, &tmB, lb, n0 + c * 64, k0, z);
+            }
+          } else {
+            mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_3d(sa, &tmA, full_bar + s, k0, m0, z);  // box {64 k, 128 m, 1}
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_3d(sa + c * 8192, &tmA, full_bar + s, m0 + c * 64, k0, z);  // {64 m, 64 k, 1}
+            }
+            if (!B_MN) {
+              tma_load_3d(sb, &tmB, full_bar + s, k0, n0, z);  // box {64 k, BN n, 1}
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c) tma_load_3d(sb + c * 8192, &tmB, full_bar + s, n0 + c * 64, k0, z);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
+    if (lane == 0 && cta_rank == 0) {
+      // ===== MMA issuer (the leader CTA of a pair issues for both) =====
       // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
       // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
       uint32_t it = 0, tcount = 0;
-      for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x, ++tcount) {
+      for (int unit = unit0; unit < p.total_tiles; unit += ustep, ++tcount) {
         const int split = unit % p.splits;
         const int kb_lo = split * p.kb_per_split, kb_hi = min(num_kb, kb_lo + p.kb_per_split);
         const uint32_t slot = tcount & 1, use = tcount >> 1;
@@ -482,11 +572,16 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
             // MN-major: advance 16 k-rows = two 1024 B swizzle atoms.
             const uint64_t ad = make_smem_desc(sa + (A_MN ? k * 2048 : k * 32), p.a_lbo, p.a_sbo);
             const uint64_t bd = make_smem_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
-            umma_f16(acc, ad, bd, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+            if (CTAS == 2) umma_f16_pair(acc, ad, bd, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+            else umma_f16(acc, ad, bd, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (CTAS == 2) umma_commit_pair(empty_bar + s);
+          else umma_commit(empty_bar + s);
         }
-        umma_commit(tmem_full_bar + slot);  // accumulator complete
+        // accumulator complete
+        if (CTAS == 2) umma_commit_pair(tmem_full_bar + slot);
+        else umma_commit(tmem_full_bar + slot);
       }
     }
     __syncwarp();
@@ -503,7 +598,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
         prefetch_tmap(&tmX);
       }
 #define DX_EPI(MASKV) \
-  staged_epilogue<BN, MASKV>(e0, p, &tmR, &tmX, tmem_base, wstg, wbias, sfull, q, chalf, lane, tmem_full_bar, tmem_empty_bar)
+  staged_epilogue<BN, MASKV, CTAS>(e0, p, &tmR, &tmX, tmem_base, wstg, wbias, sfull, q, chalf, lane, tmem_full_bar, tmem_empty_bar)
       switch (p.epi_mask) {
         case 0: DX_EPI(0); break;
         case DX_M_BIAS: DX_EPI(DX_M_BIAS); break;
@@ -518,10 +613,11 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
 #undef DX_EPI
     } else {
       uint32_t tcount = 0;
-      for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x, ++tcount) {
+      const uint32_t empty_remote = CTAS == 2 ? mapa_u32(smem_u32(tmem_empty_bar), 0) : 0;
+      for (int unit = unit0; unit < p.total_tiles; unit += ustep, ++tcount) {
         const int tile = unit / p.splits;
         const int n0 = (tile % p.tiles_n) * BN;
-        const int m0 = ((tile / p.tiles_n) % p.tiles_m) * BM;
+        const int m0 = ((tile / p.tiles_n) % p.tiles_m) * (BM * CTAS) + (int)cta_rank * BM;
         const int z = tile / (p.tiles_n * p.tiles_m);
         const uint32_t slot = tcount & 1, use = tcount >> 1;
         const uint32_t acc = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
@@ -551,14 +647,22 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
         // this warp has finished reading the accumulator: hand the TMEM slot back to the MMA issuer
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty_bar + slot);
+        if (lane == 0) {
+          if (CTAS == 2) mbar_arrive_cluster(empty_remote + slot * 8);
+          else mbar_arrive(tmem_empty_bar + slot);
+        }
         if (row_ok) dx_epilogue_flush_row(e, m, rs, rd);
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CTAS == 2) {
+    cluster_sync_all();   // the peer may still be reading this CTA's operands / signalling its barriers
+    if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -598,16 +702,16 @@ int make_tmap(CUtensorMap* map, const void* base, long long inner, long long out
   return DX_OK;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED, int CTAS = 1>
 int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr,
                const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
-  const int smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 512 /*barriers*/ +
+  const int smem = STAGES * (BM * BK * 2 + (BN / CTAS) * BK * 2) + 1024 /*align slack*/ + 512 /*barriers*/ +
                    (STAGED ? NEPI * (p.stage_bufs * STG_BYTES + 512) : 0);
   if (smem > 232448) {
     dx_set_error("dx_gemm_tc: tile config BN=%d stages=%d needs %d B of shared memory", BN, STAGES, smem);
     return DX_ERR_UNSUPPORTED;
   }
-  auto kern = dx_gemm_tc_kernel<BN, STAGES, A_MN, B_MN, STAGED>;
+  auto kern = dx_gemm_tc_kernel<BN, STAGES, A_MN, B_MN, STAGED, CTAS>;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -615,7 +719,7 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   }
   TcParams pp = p;
   pp.tiles_n = dx_ceil_div(d->N, BN);
-  pp.tiles_m = dx_ceil_div(d->M, BM);
+  pp.tiles_m = dx_ceil_div(d->M, BM * CTAS);
   long long total = (long long)pp.tiles_n * pp.tiles_m * (d->batch > 1 ? d->batch : 1);
   static int num_sms = 0;
   if (!num_sms) {
@@ -628,13 +732,14 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   const int num_kb = dx_ceil_div(d->K, BK);
   const bool pure_acc = d->accumulate && d->out_dtype == DX_F32 && !d->out2 && !d->res && !d->aux && !d->cx && !d->bias &&
                         !d->row_scale && !d->row_sumsq && !d->row_dot && d->act == DX_ACT_NONE;
-  const double eff1 = (double)total / ((double)((total + num_sms - 1) / num_sms) * num_sms);   // wave efficiency unsplit
+  const int workers = num_sms / CTAS;   // CTAs, or CTA pairs
+  const double eff1 = (double)total / ((double)((total + workers - 1) / workers) * workers);   // wave efficiency unsplit
   if (!STAGED && pure_acc && eff1 < 0.85 && num_kb >= 64) {
     // smallest split whose work units fill >= 85 % of whole waves (atomic traffic grows with the split), else the best
     double best = eff1;
     for (int sp = 2; sp <= 8 && num_kb / sp >= 32; ++sp) {
       const long long u = total * sp;
-      const double eff = (double)u / ((double)((u + num_sms - 1) / num_sms) * num_sms);
+      const double eff = (double)u / ((double)((u + workers - 1) / workers) * workers);
       if (eff > best + 0.04) { best = eff; pp.splits = sp; }
       if (eff >= 0.85) break;
     }
@@ -647,6 +752,24 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
     return DX_ERR_ARG;
   }
   pp.total_tiles = (int)total;
+  if (CTAS == 2) {
+    // one CTA pair (cluster of 2 = the two SMs of a TPC) per 256-row tile; persistent over min(pairs, tiles)
+    const int pairs = (int)(total < workers ? total : workers);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DX_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, tx, pp, e));
+    return DX_OK;
+  }
   const int ctas_per_sm = smem <= 113 * 1024 ? 2 : 1;   // persistent grid: fill every SM, no more
   const int grid = (int)(total < (long long)num_sms * ctas_per_sm ? total : (long long)num_sms * ctas_per_sm);
   kern<<<grid, NTHREADS, smem, stream>>>(ta, tb, tr, tx, pp, e);
@@ -654,9 +777,23 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   return DX_OK;
 }
 
+// CTA-pair instantiations exist for the three operand layouts of the deep-K GEMMs of the path
 template <bool A_MN, bool B_MN, bool STAGED>
-int launch_major(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& ta, const CUtensorMap& tb,
+constexpr bool pair_instantiated() { return (!A_MN && STAGED) || (A_MN && B_MN && !STAGED); }
+
+template <bool A_MN, bool B_MN, bool STAGED>
+int launch_major(const dx_gemm_desc* d, int bn, int stages, int ctas, const CUtensorMap& ta, const CUtensorMap& tb,
                  const CUtensorMap& tr, const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
+  if (ctas == 2) {
+    if constexpr (pair_instantiated<A_MN, B_MN, STAGED>()) {
+      if (bn == 256 && stages == 6) return launch_cfg<256, 6, A_MN, B_MN, STAGED, 2>(d, ta, tb, tr, tx, p, e, stream);
+      if (bn == 256 && stages == 4) return launch_cfg<256, 4, A_MN, B_MN, STAGED, 2>(d, ta, tb, tr, tx, p, e, stream);
+      if (bn == 192 && stages == 6) return launch_cfg<192, 6, A_MN, B_MN, STAGED, 2>(d, ta, tb, tr, tx, p, e, stream);
+    }
+    dx_set_error("dx_gemm_tc: no CTA-pair instance for BN=%d stages=%d a_mn=%d b_mn=%d staged=%d", bn, stages, (int)A_MN,
+                 (int)B_MN, (int)STAGED);
+    return DX_ERR_UNSUPPORTED;
+  }
   if (bn == 256 && stages == 4) return launch_cfg<256, 4, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
   if (bn == 256 && stages == 3) return launch_cfg<256, 3, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
   if (bn == 256 && stages == 2) return launch_cfg<256, 2, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
@@ -671,13 +808,13 @@ int launch_major(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& t
 }
 
 template <bool STAGED>
-int launch_staged(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr,
-                  const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
-  if (!d->a_mn && !d->b_mn) return launch_major<false, false, STAGED>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
-  if (!d->a_mn && d->b_mn) return launch_major<false, true, STAGED>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
+int launch_staged(const dx_gemm_desc* d, int bn, int stages, int ctas, const CUtensorMap& ta, const CUtensorMap& tb,
+                  const CUtensorMap& tr, const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
+  if (!d->a_mn && !d->b_mn) return launch_major<false, false, STAGED>(d, bn, stages, ctas, ta, tb, tr, tx, p, e, stream);
+  if (!d->a_mn && d->b_mn) return launch_major<false, true, STAGED>(d, bn, stages, ctas, ta, tb, tr, tx, p, e, stream);
   if constexpr (!STAGED) {   // MN-major A only occurs in dW GEMMs (fp32 accumulate, direct epilogue): no staged instances
-    if (d->a_mn && !d->b_mn) return launch_major<true, false, STAGED>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
-    return launch_major<true, true, STAGED>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
+    if (d->a_mn && !d->b_mn) return launch_major<true, false, STAGED>(d, bn, stages, ctas, ta, tb, tr, tx, p, e, stream);
+    return launch_major<true, true, STAGED>(d, bn, stages, ctas, ta, tb, tr, tx, p, e, stream);
   }
   dx_set_error("dx_gemm_tc: internal: staged epilogue with MN-major A");
   return DX_ERR_UNSUPPORTED;
@@ -733,11 +870,28 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
       break;
     }
   }
+  // CTA pairs (256 x 256 tiles over two SMs) for the deep-K contractions: they are bound by the L2 -> SM operand feed with
+  // single-CTA tiles.  DX_GEMM_PAIR=0 disables, =1 forces the pair kernel wherever an instance exists.
+  int ctas = 1;
+  {
+    const bool inst = (!d->a_mn && staged) || (d->a_mn && d->b_mn && !staged);
+    // a half-empty last 256-row tile wastes a quarter of the MMA work of a short M (dW of the 384-wide QKV weight)
+    const bool m_ok = d->M >= 2048 || (d->M % 256) == 0 || (d->M % 256) > 128;
+    const bool legal = !user_cfg && inst && (bn == 256 || bn == 192) && batch == 1 && d->M > 128 && m_ok;
+    int mode = -1;
+    if (const char* env = getenv("DX_GEMM_PAIR")) mode = atoi(env);
+    if (legal && (mode == 1 || (mode != 0 && d->K >= 1024))) {
+      const int budget = 232448 - 1536 - (staged ? NEPI * (nbufs * STG_BYTES + 512) : 0);
+      const int stage_bytes = (BM + bn / 2) * BK * 2;
+      const int st2 = 6 * stage_bytes <= budget ? 6 : ((bn == 256 && 4 * stage_bytes <= budget) ? 4 : 0);
+      if (st2) { ctas = 2; stages = st2; }
+    }
+  }
   CUtensorMap ta, tb;
   if (!d->a_mn) rc = make_tmap(&ta, d->A, d->K, d->M, d->lda, batch, d->a_bs, BK, BM);
   else rc = make_tmap(&ta, d->A, d->M, d->K, d->lda, batch, d->a_bs, 64, BK);
   if (rc) return rc;
-  if (!d->b_mn) rc = make_tmap(&tb, d->B, d->K, d->N, d->ldb, batch, d->b_bs, BK, bn);
+  if (!d->b_mn) rc = make_tmap(&tb, d->B, d->K, d->N, d->ldb, batch, d->b_bs, BK, bn / ctas);
   else rc = make_tmap(&tb, d->B, d->N, d->K, d->ldb, batch, d->b_bs, 64, BK);
   if (rc) return rc;
   TcParams p;
@@ -763,6 +917,6 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
                 : make_tmap(&tx, d->cx, d->N, d->M, d->ldc, batch, d->cx_bs, 64, 32);
     if (rc) return rc;
   }
-  if (staged) return launch_staged<true>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
-  return launch_staged<false>(d, bn, stages, ta, tb, tr, tx, p, e, stream);
+  if (staged) return launch_staged<true>(d, bn, stages, ctas, ta, tb, tr, tx, p, e, stream);
+  return launch_staged<false>(d, bn, stages, ctas, ta, tb, tr, tx, p, e, stream);
 }
