@@ -177,6 +177,10 @@ def main():
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: native libraries that print to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     import torch.distributed as dist
@@ -229,6 +233,28 @@ def main():
             traceback.print_exc(file=sys.stderr)
             graph_err, gstep = repr(ex)[:200], None
             torch.cuda.synchronize()
+
+    # SURVEY §8(d) also asks for the step WITHOUT the optimizer (fwd + loss + bwd + all-reduce): a second captured graph
+    def train_fn_noopt():
+        opt.zero_grad()
+        red.start_step()
+        y_hat = model.forward((static["xs_static"], static["xs_ts"], static["xs_times"], n_steps_static))
+        loss = model._supervised_loss(y_hat, static["y"])
+        loss.backward()
+        red.finish()
+        return loss
+
+    gstep_noopt = None
+    if gstep is not None:
+        try:
+            gstep_noopt = CudaGraphStep(train_fn_noopt, static, warmup=3)
+        except Exception as ex:
+            print("no-optimizer graph not captured:", repr(ex)[:200], file=sys.stderr)
+            torch.cuda.synchronize()
+
+    def step_noopt(i):
+        x, y = dev_batches[i % nb]
+        return gstep_noopt(xs_static=x[0], xs_ts=x[1], xs_times=x[2], y=y)
 
     def step_resident(i):
         if gstep is None:
@@ -316,6 +342,11 @@ def main():
     e2e_collect()
     e2e_state["losses"].clear()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+    ms_noopt = None
+    if gstep_noopt is not None:
+        for i in range(3):
+            step_noopt(i)
+        ms_noopt, _, _ = timed(step_noopt, args.steps)
     assert len(e2e_state["losses"]) == args.steps and all(l == l for l in e2e_state["losses"]), "e2e: a loss was not read back"
 
     if rank == 0:
@@ -369,10 +400,13 @@ def main():
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
             "model_tflops": value * train_flops_per_sample() / 1e12,
             "model_frac_of_bf16_peak": value * train_flops_per_sample() / 1e12 / (world * pk["bf16_tflops_sustained"]),
+            "fwd_bwd_allreduce_only": None if ms_noopt is None else {
+                "value": world * B * args.steps / (ms_noopt / 1e3), "unit": "samples/s", "ms_per_step": ms_noopt / args.steps},
             "allreduce_buckets_per_step": red.launched, "host_enqueue_ms_per_step": host_ms,
             "cuda_graph": gstep is not None, "cuda_graph_error": graph_err, "eager_ms_per_step": ms_eager / args.steps,
         }
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         # The captured step graph holds NCCL kernels of this communicator; tearing the communicator down underneath it
         # (destroy_process_group / interpreter shutdown order) was seen to block forever on 2 GPUs.  Everything is

@@ -213,6 +213,15 @@ int dx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
 int dx_sumsq(const float* x, int64_t n, float* out, void* stream);
 int dx_clip_factor(const float* sumsq, float max_norm, float* clip, void* stream);
 
+/* ---- evaluation metrics --------------------------------------------------------------------------------
+ * Replaces the host-side scoring of training_duett/evaluator.py:22-35 (torch.sigmoid -> .numpy() -> sklearn
+ * roc_auc_score / average_precision_score).  out[0] = AUROC (trapezoid over the ROC points of the distinct-score
+ * thresholds), out[1] = AUPRC (step-wise average precision), out[2] = number of positives, out[3] = n; NaN where sklearn
+ * raises (single-class input).  key_ws / lab_ws: npad floats of scratch each, npad = n rounded up to a power of two.
+ * apply_sigmoid = 1 ranks sigmoid(logits) computed in fp32 like the reference, 0 ranks the raw scores. */
+int dx_binary_auc(const float* logits, const float* labels, int64_t n, float* key_ws, float* lab_ws, int64_t npad,
+                  int apply_sigmoid, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -410,5 +410,21 @@ def sumsq(x, out):
     _call("dx_sumsq", _p(x), x.numel(), _p(out))
 
 
+def binary_auc(logits, labels, apply_sigmoid=True):
+    """AUROC / AUPRC of a binary scorer on the device -> float64 tensor [auroc, auprc, n_pos, n] (training_duett/
+    evaluator.py:22-35 semantics: sklearn roc_auc_score / average_precision_score of sigmoid(logits))."""
+    logits = logits.reshape(-1).float().contiguous()
+    labels = labels.reshape(-1).float().contiguous()
+    _chk(logits, torch.float32)
+    n = logits.numel()
+    if labels.numel() != n or n == 0:
+        raise L.DxError(f"binary_auc: {n} logits vs {labels.numel()} labels")
+    npad = 1 << max(1, (n - 1).bit_length())
+    ws = torch.empty((2, npad), device=logits.device, dtype=torch.float32)
+    out = torch.empty(4, device=logits.device, dtype=torch.float64)
+    _call("dx_binary_auc", _p(logits), _p(labels), n, _p(ws[0]), _p(ws[1]), npad, int(bool(apply_sigmoid)), _p(out))
+    return out
+
+
 def clip_factor(sumsq_t, max_norm, clip):
     _call("dx_clip_factor", _p(sumsq_t), float(max_norm), _p(clip))

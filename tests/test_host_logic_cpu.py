@@ -168,3 +168,26 @@ def test_state_dict_round_trip_and_tolerant_checkpoint_loading(emu, tmp_path):
     assert torch.equal(got["time_transformers.1.layers.0.1.to_k.weight"], G["param"]["time_transformers.1.layers.0.1.to_k.weight"])
     assert got["head.0.weight"].shape == (64, 48)
     assert m.d_representation == 48
+
+
+def test_evaluate_binary_surface(emu):
+    """evaluate_binary(model, loader, device, forward_fn) -> {"auroc","auprc","n","pos_frac"} like the reference's
+    evaluator (training_duett/evaluator.py:10-37); scoring itself is the kernel's job (emulated here by its contract)."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from multimodal_edema_prediction_b200.training_duett import evaluator
+
+    class Dummy(torch.nn.Module):
+        def forward(self, x):
+            return x * 2.0 - 0.3
+
+    g = torch.Generator().manual_seed(0)
+    batches = [{"x": torch.randn(17, generator=g), "y": (torch.rand(17, generator=g) < 0.4).float()} for _ in range(5)]
+    res = evaluator.evaluate_binary(Dummy(), batches, torch.device("cpu"), lambda m, b, dev: {"logits": m(b["x"]), "y": b["y"]})
+    z = torch.cat([b["x"] * 2.0 - 0.3 for b in batches])
+    y = torch.cat([b["y"] for b in batches]).numpy()
+    assert res["n"] == 85 and abs(res["pos_frac"] - y.mean()) < 1e-12
+    assert abs(res["auroc"] - roc_auc_score(y, torch.sigmoid(z).numpy())) < 1e-12
+    assert abs(res["auprc"] - average_precision_score(y, torch.sigmoid(z).numpy())) < 1e-12
+    assert set(res) == {"auroc", "auprc", "n", "pos_frac"}
+    for name in ("make_teacher_forward", "make_teacher_aux_forward", "make_student_forward"):
+        assert callable(getattr(evaluator, name)())

@@ -326,3 +326,28 @@ def test_adamw_matches_torch(ops):
     clip = torch.zeros(1, device="cuda")
     ops.clip_factor(ss, 1.0, clip)
     assert rel(clip, torch.clamp(1.0 / (g.norm() + 1e-6), max=1.0)) < 1e-5
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 4096, 5000])
+def test_binary_auc_vs_sklearn(ops, n):
+    """dx_binary_auc against sklearn (the reference's scorer, training_duett/evaluator.py:22-35): heavy ties, raw-score mode
+    is exact to float64 rounding; sigmoid mode ranks fp32 sigmoid(logits) like the reference."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    g = torch.Generator().manual_seed(n)
+    z = torch.randn(n, generator=g)
+    zq = (z * 4).round() / 4                      # many exact ties
+    y = (torch.rand(n, generator=g) < 0.35).float()
+    if n > 1:
+        y[0], y[1] = 1.0, 0.0                      # both classes present
+    for scores, sig in ((zq, False), (z, True), (zq, True)):
+        out = ops.binary_auc(scores.cuda(), y.cuda(), apply_sigmoid=sig).cpu()
+        p = (torch.sigmoid(scores) if sig else scores).numpy()
+        assert out[2] == y.sum() and out[3] == n
+        if n == 1:
+            assert torch.isnan(out[0])
+            continue
+        tol = 1e-6 if sig else 1e-12
+        assert abs(float(out[0]) - roc_auc_score(y.numpy(), p)) < tol
+        assert abs(float(out[1]) - average_precision_score(y.numpy(), p)) < tol
+    ones = ops.binary_auc(z.cuda(), torch.ones(n).cuda()).cpu()
+    assert torch.isnan(ones[0])                    # roc_auc_score raises on a single class; the reference maps that to NaN

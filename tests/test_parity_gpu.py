@@ -256,6 +256,14 @@ def test_auroc_on_fixed_synthetic_eval_set(mode, dauc):
     a_cuda = roc_auc_score(y, torch.sigmoid(zs).numpy())
     a_ref = roc_auc_score(y, torch.sigmoid(zr).numpy())
     assert abs(a_cuda - a_ref) < dauc, (a_cuda, a_ref)
+    # the same set through the device-side evaluator (evaluate_binary surface of training_duett/evaluator.py:10-37)
+    from multimodal_edema_prediction_b200.training_duett import evaluator
+    loader = [{"x_ts": data["x_ts"][i:i + bs], "x_static": data["x_static"][i:i + bs], "bin_ends": data["bin_ends"][i:i + bs],
+               "y": torch.from_numpy(y[i:i + bs])} for i in range(0, N, bs)]
+    res = evaluator.evaluate_binary(student, loader, torch.device("cuda"), evaluator.make_student_forward())
+    # second forward pass of the same model: fp32 logits repeat to ~1e-7 (atomic row sums), which can flip a near-tie - one
+    # pair of the 492 x 532 is 3.8e-6 of AUROC; bf16 logits move by rounding flips
+    assert res["n"] == N and abs(res["auroc"] - a_cuda) < (1e-5 if mode == "fp32" else dauc), (res, a_cuda)
     # logits: fp32 within the north-star 1e-3.  In bf16 the default-init logits are ~0.1 with a large common-mode part, so
     # ||dz||/||z|| is dominated by cancellation (the reference's own bf16 run is off by 37 % on this measure);
     # compare the sample-to-sample variation that AUROC actually ranks on.
