@@ -16,8 +16,6 @@ namespace {
 
 constexpr int NT = 256;
 
-constexpr int RU = 4;   // independent 16 B (bf16) / 32 B (f32) loads in flight per thread before the first use
-
 template <typename T>
 __global__ void __launch_bounds__(NT) relayout_fwd_kernel(const T* __restrict__ src, const float* __restrict__ src_rowsq,
                                                          const float* __restrict__ g, const float* __restrict__ pos_b,
@@ -30,46 +28,31 @@ __global__ void __launch_bounds__(NT) relayout_fwd_kernel(const T* __restrict__ 
   const float c = g ? sqrtf((float)Q * (float)d) * g[0] : 1.f;
   float ss = 0.f;
   T* drow = dst + (long long)row * P * d;
-  const T* sbase = src + ((long long)b * P * Q + q) * d;
-  for (int i0 = threadIdx.x; i0 < nvec; i0 += NT * RU) {
-    float v[RU][8], sc[RU];
+  for (int i = threadIdx.x; i < nvec; i += NT) {
+    const int e = i << 3;
+    const int p = e / d, dd = e - p * d;
+    float v[8];
+    dx_ld8(src + (((long long)b * P + p) * Q + q) * d + dd, v);
+    if (src_rowsq) {
+      const float s = c / fmaxf(sqrtf(src_rowsq[b * P + p]), 1e-12f);
 #pragma unroll
-    for (int u = 0; u < RU; ++u) {
-      const int i = i0 + u * NT;
-      if (i < nvec) {
-        const int e = i << 3;
-        const int p = e / d, dd = e - p * d;
-        dx_ld8(sbase + (long long)p * Q * d + dd, v[u]);
-        sc[u] = src_rowsq ? src_rowsq[b * P + p] : 1.f;
-      }
+      for (int j = 0; j < 8; ++j) v[j] *= s;
+    }
+    if (pos_b) {
+      float pv[8];
+      dx_ld8(pos_b + (long long)q * P * d + e, pv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += pv[j];
+    }
+    if (pos_n) {
+      float pv[8];
+      dx_ld8(pos_n + (long long)row * P * d + e, pv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += pv[j];
     }
 #pragma unroll
-    for (int u = 0; u < RU; ++u) {
-      const int i = i0 + u * NT;
-      if (i < nvec) {
-        const int e = i << 3;
-        if (src_rowsq) {
-          const float s = c / fmaxf(sqrtf(sc[u]), 1e-12f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[u][j] *= s;
-        }
-        if (pos_b) {
-          float pv[8];
-          dx_ld8(pos_b + (long long)q * P * d + e, pv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[u][j] += pv[j];
-        }
-        if (pos_n) {
-          float pv[8];
-          dx_ld8(pos_n + (long long)row * P * d + e, pv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[u][j] += pv[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss += v[u][j] * v[u][j];
-        dx_st8(drow + e, v[u]);
-      }
-    }
+    for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
+    dx_st8(drow + e, v);
   }
   if (dst_rowsq) {
     ss = dx_block_sum(ss, sh);
@@ -87,28 +70,17 @@ __global__ void __launch_bounds__(NT) relayout_bwd_kernel(const T* __restrict__ 
   const int b = row / P, p = row % P;
   const int nvec = (Q * d) >> 3;
   const long long roff = (long long)row * Q * d;
-  const T* gbase = gdst + ((long long)b * Q * P + p) * d;
   const bool norm = src_rowsq != nullptr;
   float dot = 0.f;
   if (norm) {
-    for (int i0 = threadIdx.x; i0 < nvec; i0 += NT * RU) {
-      float gy[RU][8], x[RU][8];
+    for (int i = threadIdx.x; i < nvec; i += NT) {
+      const int e = i << 3;
+      const int q = e / d, dd = e - q * d;
+      float gy[8], x[8];
+      dx_ld8(gdst + (((long long)b * Q + q) * P + p) * d + dd, gy);
+      dx_ld8(src + roff + e, x);
 #pragma unroll
-      for (int u = 0; u < RU; ++u) {
-        const int i = i0 + u * NT;
-        if (i < nvec) {
-          const int e = i << 3;
-          const int q = e / d, dd = e - q * d;
-          dx_ld8(gbase + (long long)q * P * d + dd, gy[u]);
-          dx_ld8(src + roff + e, x[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < RU; ++u)
-        if (i0 + u * NT < nvec) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dot += gy[u][j] * x[u][j];
-        }
+      for (int j = 0; j < 8; ++j) dot += gy[j] * x[j];
     }
     dot = dx_block_sum(dot, sh);
   }
@@ -121,29 +93,18 @@ __global__ void __launch_bounds__(NT) relayout_bwd_kernel(const T* __restrict__ 
     k = dot / nsq;
     if (threadIdx.x == 0 && dg) atomicAdd(dg, dot * c * inv_n);
   }
-  for (int i0 = threadIdx.x; i0 < nvec; i0 += NT * RU) {
-    float gy[RU][8], x[RU][8];
+  for (int i = threadIdx.x; i < nvec; i += NT) {
+    const int e = i << 3;
+    const int q = e / d, dd = e - q * d;
+    float gy[8];
+    dx_ld8(gdst + (((long long)b * Q + q) * P + p) * d + dd, gy);
+    if (norm) {
+      float x[8];
+      dx_ld8(src + roff + e, x);
 #pragma unroll
-    for (int u = 0; u < RU; ++u) {
-      const int i = i0 + u * NT;
-      if (i < nvec) {
-        const int e = i << 3;
-        const int q = e / d, dd = e - q * d;
-        dx_ld8(gbase + (long long)q * P * d + dd, gy[u]);
-        if (norm) dx_ld8(src + roff + e, x[u]);
-      }
+      for (int j = 0; j < 8; ++j) gy[j] = s * (gy[j] - x[j] * k);
     }
-#pragma unroll
-    for (int u = 0; u < RU; ++u) {
-      const int i = i0 + u * NT;
-      if (i < nvec) {
-        if (norm) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) gy[u][j] = s * (gy[u][j] - x[u][j] * k);
-        }
-        dx_st8(dsrc + roff + (i << 3), gy[u]);
-      }
-    }
+    dx_st8(dsrc + roff + e, gy);
   }
 }
 
