@@ -112,6 +112,10 @@ int dx_colsum(const void* X, int64_t ld, int M, int64_t N, float* out, int accum
 /* y (+)= alpha*x over n elements (n % 8 == 0) — accumulation of per-layer time-embedding gradients. */
 int dx_axpy(const void* x, void* y, int64_t n, float alpha, int accumulate, int dtype, void* stream);
 /* dtype conversion of a dense buffer (fp32 master weights -> bf16 operands; autocast's casts). */
+/* y = xs[0] + ... + xs[count-1] (1 <= count <= 8 tensors of n elements, n % 8 == 0), summed in fp32 and rounded once: the
+ * gradient of the time embedding is the sum of the time encoders' input gradients of all layers (autograd accumulation of
+ * `time_embeddings` at duett/duett.py:278). */
+int dx_sum_n(const void* const* xs, int count, void* y, int64_t n, int dtype, void* stream);
 int dx_cast(const void* x, int x_dtype, void* y, int y_dtype, int64_t n, void* stream);
 /* out[i] = c*g[0]/max(sqrt(rowsq[i]),1e-12): x_transformers ScaleNorm row scale (duett/duett.py:95-105). */
 int dx_scalenorm_scale(const float* rowsq, const float* g, float c, float* out, int N, void* stream);

@@ -181,13 +181,13 @@ class DuettEncodeFn(torch.autograd.Function):
         dx2 = ops.relayout_bwd(gout.view(B * T1, 1, 1, Ep), B * T1, 1, 1, Ep, src=ct.x2 if fn else None,
                                src_rowsq=ct.rowsq2 if fn else None, g=det[gname] if fn else None,
                                dg=sinks.get(gname) if fn else None).view(B * T1, Ep)
-        dte = torch.zeros((B, T1, Ep), device=dev, dtype=at) if ctx.te_requires_grad else None
+        dx_ts = []     # time-encoder input gradients of every layer: their sum is the time-embedding gradient
         for l in reversed(range(L)):
             ce, ct = encs[l]
             pt = _enc_params(det, f"time_transformers.{l}", at)
             dx_t = encoder_bwd(ct, dx2, pt, _enc_sinks(sinks, f"time_transformers.{l}"), heads, cfgd)   # [B*T1, Ep]
-            if dte is not None:
-                ops.axpy(dx_t, dte, 1.0, accumulate=True)
+            if ctx.te_requires_grad:
+                dx_ts.append(dx_t)
             if GRAD_READY_HOOK is not None:
                 GRAD_READY_HOOK(f"time_transformers.{l}")
             # time-major grad -> event-major grad of the event encoder's un-normalised output (+ its final norm)
@@ -209,6 +209,15 @@ class DuettEncodeFn(torch.autograd.Function):
                                        dg=sinks.get(gname) if fn else None).view(B * T1, Ep)
             else:
                 dpsi0 = ops.relayout_bwd(dx_e.view(B, V1, T1, cfgd), B, T1, V1, cfgd)
+        dte = None
+        if ctx.te_requires_grad:
+            dte = (dx_ts[0] if len(dx_ts) == 1 else ops.sum_n(dx_ts) if len(dx_ts) <= 8 else None)
+            if dte is None:       # more than 8 layers: sum in groups
+                dte = ops.sum_n(dx_ts[:8])
+                for i in range(8, len(dx_ts), 7):
+                    dte = ops.sum_n([dte] + dx_ts[i:i + 7])
+            dte = dte.view(B, T1, Ep)
+        dx_ts = None
         # embedding backward
         xs_feats, emean, erstd = ctx.emb_saved
         z = lambda n: sinks[n] if n in sinks else torch.zeros_like(P[n], dtype=torch.float32)

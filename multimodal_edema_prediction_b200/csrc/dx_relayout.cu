@@ -167,6 +167,29 @@ __global__ void __launch_bounds__(NT) axpy_kernel(const T* __restrict__ x, T* __
   }
 }
 
+// y = x0 + x1 + ... (up to 8 addends, summed in fp32 in argument order, rounded once)
+struct SumArgs {
+  const void* x[8];
+  int n;
+};
+template <typename T>
+__global__ void __launch_bounds__(NT) sum_n_kernel(SumArgs a, T* __restrict__ y, long long nvec) {
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < nvec; i += (long long)gridDim.x * NT) {
+    float acc[8];
+    dx_ld8(reinterpret_cast<const T*>(a.x[0]) + i * 8, acc);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      if (k < a.n) {
+        float b[8];
+        dx_ld8(reinterpret_cast<const T*>(a.x[k]) + i * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += b[j];
+      }
+    }
+    dx_st8(y + i * 8, acc);
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(NT) cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
   const long long nvec = n >> 3;
@@ -250,6 +273,24 @@ int dx_axpy(const void* x, void* y, int64_t n, float alpha, int accumulate, int 
   if (grid <= 0) return DX_OK;
   if (dtype == DX_BF16) axpy_kernel<bf16><<<grid, NT, 0, st>>>((const bf16*)x, (bf16*)y, nvec, alpha, accumulate);
   else axpy_kernel<float><<<grid, NT, 0, st>>>((const float*)x, (float*)y, nvec, alpha, accumulate);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
+int dx_sum_n(const void* const* xs, int count, void* y, int64_t n, int dtype, void* stream) {
+  DX_CHECK_ARG(xs && y && count >= 1 && count <= 8 && n % 8 == 0, "dx_sum_n: 1..8 addends, n %% 8 == 0");
+  SumArgs a;
+  a.n = count;
+  for (int k = 0; k < 8; ++k) {
+    a.x[k] = k < count ? xs[k] : nullptr;
+    DX_CHECK_ARG(k >= count || (xs[k] && (uintptr_t)xs[k] % 16 == 0), "dx_sum_n: addends must be non-null and 16 B aligned");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nvec = n >> 3;
+  long long gl = (nvec + NT - 1) / NT; const int grid = (int)(gl < 148 * 8 ? gl : 148 * 8);
+  if (grid <= 0) return DX_OK;
+  if (dtype == DX_BF16) sum_n_kernel<bf16><<<grid, NT, 0, st>>>(a, (bf16*)y, nvec);
+  else sum_n_kernel<float><<<grid, NT, 0, st>>>(a, (float*)y, nvec);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }

@@ -101,6 +101,19 @@ def axpy(x, y, alpha=1.0, accumulate=True):
     _call("dx_axpy", _p(x), _p(y), x.numel(), float(alpha), int(accumulate), _dt(x))
 
 
+def sum_n(tensors):
+    """Sum of 1..8 same-shape tensors (fp32 accumulation, one rounding) -> new tensor."""
+    import ctypes
+    t0 = tensors[0]
+    for t in tensors:
+        _chk(t)
+        assert t.shape == t0.shape and t.dtype == t0.dtype
+    y = torch.empty_like(t0)
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    _call("dx_sum_n", arr, len(tensors), _p(y), t0.numel(), _dt(t0))
+    return y
+
+
 def axpy_f32(x, y, alpha):
     """y += alpha * x for small f32 vectors of any length (dx_axpy needs n % 8 == 0, so go through dx_scale/dx_colsum)."""
     _chk(x, torch.float32); _chk(y, torch.float32)

@@ -430,6 +430,13 @@ def clip_factor(sumsq_t, max_norm, clip):
     clip[0] = min(1.0, max_norm / (float(sumsq_t[0]) ** 0.5 + 1e-6))
 
 
+def sum_n(tensors):
+    acc = tensors[0].float()
+    for t in tensors[1:]:
+        acc = acc + t.float()
+    return acc.to(tensors[0].dtype)
+
+
 def binary_auc(logits, labels, apply_sigmoid=True):
     """Contract of dx_binary_auc: sklearn's definitions on sigmoid(logits) (training_duett/evaluator.py:22-35)."""
     from sklearn.metrics import average_precision_score, roc_auc_score
@@ -443,7 +450,7 @@ def binary_auc(logits, labels, apply_sigmoid=True):
     return torch.tensor([auroc, auprc, n_pos, float(len(y))], dtype=torch.float64)
 
 
-EMULATED = ["binary_auc", "gemm_", "relayout_fwd", "relayout_bwd", "colsum", "axpy", "axpy_f32", "cast", "scalenorm_scale", "rowdot_scale",
+EMULATED = ["binary_auc", "sum_n", "gemm_", "relayout_fwd", "relayout_bwd", "colsum", "axpy", "axpy_f32", "cast", "scalenorm_scale", "rowdot_scale",
             "attn_fwd", "attn_bwd", "embed_fwd", "embed_bwd", "bn2d_fwd", "bn2d_bwd", "layernorm_fwd", "layernorm_bwd",
             "mean_rows", "mean_rows_bwd", "gather_vec", "scatter_vec", "kd_loss", "bce_logits", "masked_mse_bce",
             "masked_bce_cols", "aux_residual_kl", "require_device", "act_bwd", "act_fwd", "scale_dev", "sum_div_acc", "fusion_logits",

@@ -351,3 +351,12 @@ def test_binary_auc_vs_sklearn(ops, n):
         assert abs(float(out[1]) - average_precision_score(y.numpy(), p)) < tol
     ones = ops.binary_auc(z.cuda(), torch.ones(n).cuda()).cpu()
     assert torch.isnan(ones[0])                    # roc_auc_score raises on a single class; the reference maps that to NaN
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("k", [1, 4, 8])
+def test_sum_n(ops, dt, k):
+    xs = [rnd(3, 40, 16, dtype=dt, seed=70 + i) for i in range(k)]
+    want = torch.stack([x.float().cpu() for x in xs]).sum(0)
+    got = ops.sum_n(xs)
+    assert got.dtype == dt and rel(got, want) < TOL[dt]
