@@ -373,8 +373,16 @@ def main():
                     d[0] += 1; d[1] += a.elapsed_time(z)
             json.dump({"ffma_by_shape": {k: {"launches": v[0], "ms_total": v[1]} for k, v in ffma.items()}, "steps": args.steps, "ms_per_step": ms / args.steps, "gemm_ms_per_step": tot_ms / args.steps,
                        "gemm_share_of_step": tot_ms / ms, "by_shape": table}, open(args.profile_out, "w"), indent=1)
+        # DRAM bytes per launch of the same kernel family from the committed ncu capture (not re-measured here)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_dram_bytes.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "kernel": "dx_gemm_tc_kernel (tcgen05, all launches)",
+                "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic,
+                "traffic_source": "profiles/r01_gemm_dram_bytes.json (ncu dram__bytes_read+write, mean over the step's GEMM launches)",
+                "kernel": "dx_gemm_tc_kernel (tcgen05, all launches)",
                 "launches_per_step": len(tc) / args.steps, "flops_per_launch": tot_fl / max(len(tc), 1),
                 "ms_per_launch": tot_ms / max(len(tc), 1), "share_of_step": tot_ms / ms, "peak_source": pk["source"],
                 "timed_in": "eager pass of the same step, K steps, CUDA events around every launch"}
