@@ -373,6 +373,9 @@ def main():
                     d[0] += 1; d[1] += a.elapsed_time(z)
             json.dump({"ffma_by_shape": {k: {"launches": v[0], "ms_total": v[1]} for k, v in ffma.items()}, "steps": args.steps, "ms_per_step": ms / args.steps, "gemm_ms_per_step": tot_ms / args.steps,
                        "gemm_share_of_step": tot_ms / ms, "by_shape": table}, open(args.profile_out, "w"), indent=1)
+        # the family mixes tensor-bound (deep K) and HBM-bound (K <= 512, N = dim) launches: per-launch speed of light
+        # max(flops / bf16 peak, algorithmic bytes / copy bandwidth), summed, against the measured time
+        ideal_ms = sum(max(r[2] / (pk["bf16_tflops_sustained"] * 1e12), r[3] / (pk["hbm_gbs"] * 1e9)) for r in tc) * 1e3
         # DRAM bytes per launch of the same kernel family from the committed ncu capture (not re-measured here)
         traffic = None
         try:
@@ -382,6 +385,7 @@ def main():
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic,
                 "traffic_source": "profiles/r01_gemm_dram_bytes.json (ncu dram__bytes_read+write, mean over the step's GEMM launches)",
+                "frac_of_per_launch_speed_of_light": (ideal_ms / tot_ms) if tot_ms > 0 else None,
                 "kernel": "dx_gemm_tc_kernel (tcgen05, all launches)",
                 "launches_per_step": len(tc) / args.steps, "flops_per_launch": tot_fl / max(len(tc), 1),
                 "ms_per_launch": tot_ms / max(len(tc), 1), "share_of_step": tot_ms / ms, "peak_source": pk["source"],

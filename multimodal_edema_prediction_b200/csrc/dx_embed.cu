@@ -99,7 +99,24 @@ __global__ void embed_bn_eval_kernel(const float* __restrict__ run_mean, const f
 }
 
 // ---- hidden: hn[v, b*(T+1)+t, c] ----------------------------------------------------------------------
-// grid (V, row chunks over B*(T+1)); thread = (channel pair, row lane): each thread writes 2 adjacent channels
+// grid (V, row chunks over B*(T+1)); thread = (group of 8 channels, row lane): one 16 B (bf16) store per row and thread,
+// a warp covers 4 whole rows = 512 contiguous bytes
+constexpr int CG = 8;            // channels per thread
+constexpr int RL = NT / (H / CG);   // 32 row lanes per block
+
+struct ChanConst {   // per-thread constants of its 8 channels
+  float w0[CG], w1[CG], bb[CG];
+};
+__device__ __forceinline__ ChanConst load_chan(const EmbedIn& in, int v, int c0) {
+  ChanConst k;
+#pragma unroll
+  for (int j = 0; j < CG; ++j) {
+    const int i = v * H + c0 + j;
+    k.w0[j] = in.W0[i * 2]; k.w1[j] = in.W0[i * 2 + 1]; k.bb[j] = in.b0[i];
+  }
+  return k;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(NT) embed_hidden_kernel(EmbedIn in, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -107,28 +124,28 @@ __global__ void __launch_bounds__(NT) embed_hidden_kernel(EmbedIn in, const floa
   const int v = blockIdx.x;
   const int T1 = in.T + 1;
   const int R1 = in.B * T1;
-  const int c = (threadIdx.x & 31) * 2, rl = threadIdx.x >> 5;  // 8 row lanes
+  const int c0 = (threadIdx.x & (H / CG - 1)) * CG, rl = threadIdx.x / (H / CG);
   const int r0 = blockIdx.y * rows_per_block, r1 = min(R1, r0 + rows_per_block);
-  float w0[2], w1[2], bb[2], sc[2], sf[2];
+  const ChanConst k = load_chan(in, v, c0);
+  float sc[CG], sf[CG];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int i = v * H + c + j;
-    w0[j] = in.W0[i * 2]; w1[j] = in.W0[i * 2 + 1]; bb[j] = in.b0[i];
+  for (int j = 0; j < CG; ++j) {
+    const int i = v * H + c0 + j;
     sc[j] = gamma[i] * rstd[i];
     sf[j] = beta[i] - mean[i] * sc[j];
   }
-  for (int rr = r0 + rl; rr < r1; rr += 8) {
+  for (int rr = r0 + rl; rr < r1; rr += RL) {
     const int b = rr / T1, t = rr - b * T1;
-    float o[2] = {0.f, 0.f};
+    float o[CG];
+#pragma unroll
+    for (int j = 0; j < CG; ++j) o[j] = 0.f;
     if (t < in.T) {
       float val, cnte; int idx;
       cell_inputs(in, b * in.T + t, v, val, cnte, idx);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) o[j] = fmaf(fmaxf(fmaf(w0[j], val, fmaf(w1[j], cnte, bb[j])), 0.f), sc[j], sf[j]);
+      for (int j = 0; j < CG; ++j) o[j] = fmaf(fmaxf(fmaf(k.w0[j], val, fmaf(k.w1[j], cnte, k.bb[j])), 0.f), sc[j], sf[j]);
     }
-    T* p = hn + ((long long)v * R1 + rr) * H + c;
-    dx_st(p, o[0]);
-    dx_st(p + 1, o[1]);
+    dx_st8(hn + ((long long)v * R1 + rr) * H + c0, o);
   }
 }
 
@@ -159,20 +176,27 @@ __global__ void __launch_bounds__(NT) embed_special_kernel(EmbedIn in, const flo
 
 // grads of special_embeddings[0] (MASK), [1] ([REP]) and of the tab_encoder output; one block per (sample, time row).
 // Every special cell of dpsi is zeroed afterwards (the embedding MLP outputs there were overwritten in the forward).
+// The row's V+1 cells are classified once into shared memory (1 = MASK, 2 = [REP], 3 = static column, 0 = ordinary);
+// the d-vector loop then touches the special cells only.
 template <typename T>
 __global__ void __launch_bounds__(NT) embed_special_bwd_kernel(EmbedIn in, T* __restrict__ dpsi, float* __restrict__ dsp /*[8,d]*/,
                                                               float* __restrict__ dtab /*[B,d], zeroed by the caller*/) {
+  extern __shared__ unsigned char kind[];   // [V+1]
   const int d = in.d, V = in.V, T_ = in.T;
   const int b = blockIdx.x / (T_ + 1), t = blockIdx.x % (T_ + 1);
-  for (int dd = threadIdx.x; dd < d; dd += NT) {  // threads over dd: coalesced across the d-vector
+  for (int v = threadIdx.x; v <= V; v += blockDim.x)
+    kind[v] = cell_masked(in, b, t, v) ? 1 : (t == T_ ? 2 : (v == V ? 3 : 0));
+  __syncthreads();
+  T* row = dpsi + (((long long)b * (T_ + 1) + t) * (V + 1)) * d;
+  for (int dd = threadIdx.x; dd < d; dd += blockDim.x) {  // threads over dd: coalesced across the d-vector
     float a0 = 0.f, a1 = 0.f, at = 0.f;
     for (int v = 0; v <= V; ++v) {
-      const bool masked = cell_masked(in, b, t, v);
-      if (masked || t == T_ || v == V) {
-        T* p = dpsi + ((((long long)b * (T_ + 1) + t) * (V + 1)) + v) * d + dd;
+      const int kd = kind[v];
+      if (kd) {
+        T* p = row + (long long)v * d + dd;
         const float g = dx_ld(p);
-        if (masked) a0 += g;
-        else if (t == T_) a1 += g;
+        if (kd == 1) a0 += g;
+        else if (kd == 2) a1 += g;
         else at += g;
         dx_st(p, 0.f);
       }
@@ -184,35 +208,48 @@ __global__ void __launch_bounds__(NT) embed_special_bwd_kernel(EmbedIn in, T* __
 }
 
 // dgamma[v,c] = sum_r dhn*hhat ; dbeta[v,c] = sum_r dhn   (this step's values, [2,V,H] f32, zeroed by the caller)
+// thread = (group of 8 channels, row lane): 16 B loads of dhn, a warp covers 4 whole rows
 template <typename T>
 __global__ void __launch_bounds__(NT) embed_bn_reduce_kernel(EmbedIn in, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const T* __restrict__ dhn, float* __restrict__ dgb, int rows_per_block) {
-  __shared__ float sh[2][4][H];
+  __shared__ float sh[2][RL][H + 1];
   const int v = blockIdx.x;
-  const int c = threadIdx.x & (H - 1), rl = threadIdx.x >> 6;
+  const int c0 = (threadIdx.x & (H / CG - 1)) * CG, rl = threadIdx.x / (H / CG);
   const int T1 = in.T + 1, R1 = in.B * T1;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(R1, r0 + rows_per_block);
-  const float w0 = in.W0[(v * H + c) * 2], w1 = in.W0[(v * H + c) * 2 + 1], bb = in.b0[v * H + c];
-  const float mu = mean[v * H + c], rs = rstd[v * H + c];
-  float ag = 0.f, ab = 0.f;
-  for (int rr = r0 + rl; rr < r1; rr += 4) {
+  const ChanConst k = load_chan(in, v, c0);
+  float mu[CG], rs[CG], ag[CG], ab[CG];
+#pragma unroll
+  for (int j = 0; j < CG; ++j) {
+    mu[j] = mean[v * H + c0 + j]; rs[j] = rstd[v * H + c0 + j];
+    ag[j] = 0.f; ab[j] = 0.f;
+  }
+  for (int rr = r0 + rl; rr < r1; rr += RL) {
     const int b = rr / T1, t = rr - b * T1;
     if (t == in.T) continue;
     float val, cnte; int idx;
     cell_inputs(in, b * in.T + t, v, val, cnte, idx);
-    const float h = fmaxf(fmaf(w0, val, fmaf(w1, cnte, bb)), 0.f);
-    const float g = dx_ld(dhn + ((long long)v * R1 + rr) * H + c);
-    ab += g;
-    ag = fmaf(g, (h - mu) * rs, ag);
+    float g[CG];
+    dx_ld8(dhn + ((long long)v * R1 + rr) * H + c0, g);
+#pragma unroll
+    for (int j = 0; j < CG; ++j) {
+      const float h = fmaxf(fmaf(k.w0[j], val, fmaf(k.w1[j], cnte, k.bb[j])), 0.f);
+      ab[j] += g[j];
+      ag[j] = fmaf(g[j], (h - mu[j]) * rs[j], ag[j]);
+    }
   }
-  sh[0][rl][c] = ag;
-  sh[1][rl][c] = ab;
+#pragma unroll
+  for (int j = 0; j < CG; ++j) {
+    sh[0][rl][c0 + j] = ag[j];
+    sh[1][rl][c0 + j] = ab[j];
+  }
   __syncthreads();
-  if (rl == 0) {
-    ag = sh[0][0][c] + sh[0][1][c] + sh[0][2][c] + sh[0][3][c];
-    ab = sh[1][0][c] + sh[1][1][c] + sh[1][2][c] + sh[1][3][c];
-    atomicAdd(dgb + v * H + c, ag);
-    atomicAdd(dgb + in.V * H + v * H + c, ab);
+  if (threadIdx.x < 2 * H) {
+    const int which = threadIdx.x / H, c = threadIdx.x % H;
+    float a = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < RL; ++r) a += sh[which][r][c];
+    atomicAdd(dgb + which * in.V * H + v * H + c, a);
   }
 }
 
@@ -224,45 +261,69 @@ __global__ void __launch_bounds__(NT) embed_bwd_front_kernel(EmbedIn in, const f
                                                             const float* __restrict__ dgb, float* __restrict__ dW0,
                                                             float* __restrict__ db0, float* __restrict__ dnobs, int rows_per_block,
                                                             int training) {
-  __shared__ float sh[3][4][H];
+  __shared__ float sh[3][RL][H + 1];
   __shared__ float snobs[16];
   const int v = blockIdx.x;
   const int T1 = in.T + 1, R1 = in.B * T1, R = in.B * in.T;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(R1, r0 + rows_per_block);
-  const int c = threadIdx.x & (H - 1), rl = threadIdx.x >> 6;
+  const int c0 = (threadIdx.x & (H / CG - 1)) * CG, rl = threadIdx.x / (H / CG);
   if (threadIdx.x < 16) snobs[threadIdx.x] = 0.f;
   __syncthreads();
-  const float w0 = in.W0[(v * H + c) * 2], w1 = in.W0[(v * H + c) * 2 + 1], bb = in.b0[v * H + c];
-  const float mu = mean[v * H + c], rs = rstd[v * H + c], ga = gamma[v * H + c];
-  const float mdg = training ? dgb[v * H + c] / R : 0.f;
-  const float mdb = training ? dgb[in.V * H + v * H + c] / R : 0.f;
-  float a0 = 0.f, a1 = 0.f, ab = 0.f;
-  for (int rr = r0 + rl; rr < r1; rr += 4) {
-    const int b = rr / T1, t = rr - b * T1;
-    if (t == in.T) continue;   // uniform per warp: rr depends on rl only
-    float val, cnte; int idx;
-    cell_inputs(in, b * in.T + t, v, val, cnte, idx);
-    const float pre = fmaf(w0, val, fmaf(w1, cnte, bb));
-    const float h = fmaxf(pre, 0.f);
-    const float hhat = (h - mu) * rs;
-    const float g = dx_ld(dhn + ((long long)v * R1 + rr) * H + c);
-    const float dh = ga * rs * (g - mdb - hhat * mdg);
-    const float dpre = pre > 0.f ? dh : 0.f;
-    a0 = fmaf(dpre, val, a0);
-    a1 = fmaf(dpre, cnte, a1);
-    ab += dpre;
-    const float dc = dx_warp_sum(dpre * w1);   // d(count embedding): reduce over channels (2 warps per row)
-    if ((threadIdx.x & 31) == 0) atomicAdd(&snobs[idx], dc);
+  const ChanConst k = load_chan(in, v, c0);
+  float mu[CG], rs[CG], gr[CG], mdg[CG], mdb[CG], a0[CG], a1[CG], ab[CG];
+#pragma unroll
+  for (int j = 0; j < CG; ++j) {
+    const int i = v * H + c0 + j;
+    mu[j] = mean[i]; rs[j] = rstd[i]; gr[j] = gamma[i] * rstd[i];
+    mdg[j] = training ? dgb[i] / R : 0.f;
+    mdb[j] = training ? dgb[in.V * H + i] / R : 0.f;
+    a0[j] = a1[j] = ab[j] = 0.f;
   }
-  sh[0][rl][c] = a0; sh[1][rl][c] = a1; sh[2][rl][c] = ab;
+  // uniform trip count for the whole block: the 8 lanes of a row shuffle inside the loop
+  for (int base = r0; base < r1; base += RL) {
+    const int rr = base + rl;
+    const int b = rr / T1, t = rr - b * T1;
+    const bool valid = rr < r1 && t < in.T;
+    float dc = 0.f;
+    int idx = 0;
+    if (valid) {
+      float val, cnte;
+      cell_inputs(in, b * in.T + t, v, val, cnte, idx);
+      float g[CG];
+      dx_ld8(dhn + ((long long)v * R1 + rr) * H + c0, g);
+#pragma unroll
+      for (int j = 0; j < CG; ++j) {
+        const float pre = fmaf(k.w0[j], val, fmaf(k.w1[j], cnte, k.bb[j]));
+        const float hhat = (fmaxf(pre, 0.f) - mu[j]) * rs[j];
+        const float dh = gr[j] * (g[j] - mdb[j] - hhat * mdg[j]);
+        const float dpre = pre > 0.f ? dh : 0.f;
+        a0[j] = fmaf(dpre, val, a0[j]);
+        a1[j] = fmaf(dpre, cnte, a1[j]);
+        ab[j] += dpre;
+        dc = fmaf(dpre, k.w1[j], dc);
+      }
+    }
+    // d(count embedding): reduce over the row's 64 channels = 8 consecutive lanes
+    dc += __shfl_xor_sync(0xffffffffu, dc, 1);
+    dc += __shfl_xor_sync(0xffffffffu, dc, 2);
+    dc += __shfl_xor_sync(0xffffffffu, dc, 4);
+    if (valid && c0 == 0) atomicAdd(&snobs[idx], dc);
+  }
+#pragma unroll
+  for (int j = 0; j < CG; ++j) {
+    sh[0][rl][c0 + j] = a0[j];
+    sh[1][rl][c0 + j] = a1[j];
+    sh[2][rl][c0 + j] = ab[j];
+  }
   __syncthreads();
-  if (rl == 0) {
-    a0 = sh[0][0][c] + sh[0][1][c] + sh[0][2][c] + sh[0][3][c];
-    a1 = sh[1][0][c] + sh[1][1][c] + sh[1][2][c] + sh[1][3][c];
-    ab = sh[2][0][c] + sh[2][1][c] + sh[2][2][c] + sh[2][3][c];
-    atomicAdd(dW0 + (v * H + c) * 2, a0);
-    atomicAdd(dW0 + (v * H + c) * 2 + 1, a1);
-    atomicAdd(db0 + v * H + c, ab);
+  if (threadIdx.x < 3 * H) {
+    const int which = threadIdx.x / H, c = threadIdx.x % H;
+    float a = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < RL; ++r) a += sh[which][r][c];
+    if (which == 0) atomicAdd(dW0 + (v * H + c) * 2, a);
+    else if (which == 1) atomicAdd(dW0 + (v * H + c) * 2 + 1, a);
+    else atomicAdd(db0 + v * H + c, a);
   }
   if (threadIdx.x < 16 && snobs[threadIdx.x] != 0.f) atomicAdd(dnobs + threadIdx.x, snobs[threadIdx.x]);
 }
@@ -338,8 +399,9 @@ int dx_embed_special_bwd(const float* xs, int B, int T, int V, int d, void* dpsi
   EmbedIn in{xs, B, T, V, d, nullptr, nullptr, nullptr};
   DX_CUDA(cudaMemsetAsync(dtab, 0, sizeof(float) * (size_t)B * d, st));
   const int nthr = d >= 256 ? 256 : (d >= 128 ? 128 : 64);
-  if (act_dtype == DX_BF16) embed_special_bwd_kernel<bf16><<<B * (T + 1), nthr, 0, st>>>(in, (bf16*)dpsi, dspecial, dtab);
-  else embed_special_bwd_kernel<float><<<B * (T + 1), nthr, 0, st>>>(in, (float*)dpsi, dspecial, dtab);
+  const size_t ksm = (size_t)((V + 1 + 15) & ~15);
+  if (act_dtype == DX_BF16) embed_special_bwd_kernel<bf16><<<B * (T + 1), nthr, ksm, st>>>(in, (bf16*)dpsi, dspecial, dtab);
+  else embed_special_bwd_kernel<float><<<B * (T + 1), nthr, ksm, st>>>(in, (float*)dpsi, dspecial, dtab);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }
