@@ -10,49 +10,105 @@
 //          add and the next norm's reduction in one read + one write of psi.
 // backward: dsrc[b,p,q,:] = s * (gy - src * <src,gy>/||src||^2), gy[b,p,q,:] = gdst[b,q,p,:]; dg += sum <gy,src> * c/||src||.
 #include "dx_common.cuh"
+#include <cstdlib>
 #include "../../include/duett_b200.h"
 
 namespace {
 
 constexpr int NT = 256;
 
+// raw 16 B (bf16) / 32 B (f32) vector of 8 elements, kept packed until it is used (so that several loads can be in flight)
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> { uint4 u; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void raw_ld(const bf16* p, Raw8<bf16>& r) { r.u = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void raw_ld(const float* p, Raw8<float>& r) {
+  r.a = *reinterpret_cast<const float4*>(p);
+  r.b = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<bf16>& r, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w;
+  v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+
+// One CTA per destination row.  Every thread keeps TWO independent vectors in flight (loads of both issued before either
+// is used): with one load per thread the kernel is bound by bytes in flight per SM (2048 threads x 16 B), not by HBM.
 template <typename T>
 __global__ void __launch_bounds__(NT) relayout_fwd_kernel(const T* __restrict__ src, const float* __restrict__ src_rowsq,
                                                          const float* __restrict__ g, const float* __restrict__ pos_b,
                                                          const T* __restrict__ pos_n, T* __restrict__ dst,
                                                          float* __restrict__ dst_rowsq, int B, int P, int Q, int d) {
   __shared__ float sh[33];
+  const int nt = blockDim.x;
   const int row = blockIdx.x;  // b*Q + q
   const int b = row / Q, q = row % Q;
   const int nvec = (P * d) >> 3;
   const float c = g ? sqrtf((float)Q * (float)d) * g[0] : 1.f;
   float ss = 0.f;
   T* drow = dst + (long long)row * P * d;
-  for (int i = threadIdx.x; i < nvec; i += NT) {
-    const int e = i << 3;
-    const int p = e / d, dd = e - p * d;
+  const T* sbase = src + ((long long)b * P * Q + q) * d;
+  const float* pb = pos_b ? pos_b + (long long)q * P * d : nullptr;
+  const T* pn = pos_n ? pos_n + (long long)row * P * d : nullptr;
+  const float* rsq = src_rowsq ? src_rowsq + b * P : nullptr;
+
+  auto finish = [&](int e, const Raw8<T>& rv, float rq, const Raw8<float>& rpb, const Raw8<T>& rpn) {
     float v[8];
-    dx_ld8(src + (((long long)b * P + p) * Q + q) * d + dd, v);
-    if (src_rowsq) {
-      const float s = c / fmaxf(sqrtf(src_rowsq[b * P + p]), 1e-12f);
+    raw_unpack(rv, v);
+    if (rsq) {
+      const float s = c / fmaxf(sqrtf(rq), 1e-12f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] *= s;
     }
-    if (pos_b) {
+    if (pb) {
       float pv[8];
-      dx_ld8(pos_b + (long long)q * P * d + e, pv);
+      raw_unpack(rpb, pv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += pv[j];
     }
-    if (pos_n) {
+    if (pn) {
       float pv[8];
-      dx_ld8(pos_n + (long long)row * P * d + e, pv);
+      raw_unpack(rpn, pv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += pv[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
     dx_st8(drow + e, v);
+  };
+  auto fetch = [&](int i, Raw8<T>& rv, float& rq, Raw8<float>& rpb, Raw8<T>& rpn) {
+    const int e = i << 3;
+    const int p = e / d, dd = e - p * d;
+    raw_ld(sbase + (long long)p * Q * d + dd, rv);
+    rq = rsq ? rsq[p] : 1.f;
+    if (pb) raw_ld(pb + e, rpb);
+    if (pn) raw_ld(pn + e, rpn);
+  };
+
+  int i = threadIdx.x;
+  for (; i + nt < nvec; i += 2 * nt) {
+    Raw8<T> v0, v1, n0, n1;
+    Raw8<float> p0, p1;
+    float q0, q1;
+    fetch(i, v0, q0, p0, n0);
+    fetch(i + nt, v1, q1, p1, n1);
+    finish(i << 3, v0, q0, p0, n0);
+    finish((i + nt) << 3, v1, q1, p1, n1);
+  }
+  if (i < nvec) {
+    Raw8<T> v0, n0;
+    Raw8<float> p0;
+    float q0;
+    fetch(i, v0, q0, p0, n0);
+    finish(i << 3, v0, q0, p0, n0);
   }
   if (dst_rowsq) {
     ss = dx_block_sum(ss, sh);
@@ -60,27 +116,55 @@ __global__ void __launch_bounds__(NT) relayout_fwd_kernel(const T* __restrict__ 
   }
 }
 
+// Backward: dsrc[b,p,q,:] = s * (gy - k x) with gy = gdst[b,q,p,:] (final-ScaleNorm backward of the source row) or a plain
+// transpose.  The row of gy and x is staged in shared memory by the dot-product pass (when it fits), so the second pass
+// does not go back to L2/HBM.
 template <typename T>
 __global__ void __launch_bounds__(NT) relayout_bwd_kernel(const T* __restrict__ gdst, const T* __restrict__ src,
                                                          const float* __restrict__ src_rowsq, const float* __restrict__ g,
                                                          T* __restrict__ dsrc, float* __restrict__ dg, int B, int P, int Q,
-                                                         int d) {
+                                                         int d, int stage_row) {
+  extern __shared__ __align__(16) unsigned char smraw[];
   __shared__ float sh[33];
+  const int nt = blockDim.x;
   const int row = blockIdx.x;  // b*P + p
   const int b = row / P, p = row % P;
   const int nvec = (Q * d) >> 3;
   const long long roff = (long long)row * Q * d;
+  const T* gbase = gdst + ((long long)b * Q * P + p) * d;
   const bool norm = src_rowsq != nullptr;
+  Raw8<T>* sg = reinterpret_cast<Raw8<T>*>(smraw);   // [nvec] gy, then [nvec] x  (stage_row only)
+  Raw8<T>* sx = sg + nvec;
   float dot = 0.f;
   if (norm) {
-    for (int i = threadIdx.x; i < nvec; i += NT) {
-      const int e = i << 3;
-      const int q = e / d, dd = e - q * d;
-      float gy[8], x[8];
-      dx_ld8(gdst + (((long long)b * Q + q) * P + p) * d + dd, gy);
-      dx_ld8(src + roff + e, x);
+    int i = threadIdx.x;
+    for (; i + nt < nvec; i += 2 * nt) {
+      Raw8<T> g0, g1, x0, x1;
+      const int e0 = i << 3, e1 = (i + nt) << 3;
+      const int q0 = e0 / d, q1 = e1 / d;
+      raw_ld(gbase + (long long)q0 * P * d + (e0 - q0 * d), g0);
+      raw_ld(gbase + (long long)q1 * P * d + (e1 - q1 * d), g1);
+      raw_ld(src + roff + e0, x0);
+      raw_ld(src + roff + e1, x1);
+      float a[8], c[8];
+      raw_unpack(g0, a); raw_unpack(x0, c);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dot += gy[j] * x[j];
+      for (int j = 0; j < 8; ++j) dot += a[j] * c[j];
+      raw_unpack(g1, a); raw_unpack(x1, c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot += a[j] * c[j];
+      if (stage_row) { sg[i] = g0; sx[i] = x0; sg[i + nt] = g1; sx[i + nt] = x1; }
+    }
+    if (i < nvec) {
+      Raw8<T> g0, x0;
+      const int e0 = i << 3, q0 = e0 / d;
+      raw_ld(gbase + (long long)q0 * P * d + (e0 - q0 * d), g0);
+      raw_ld(src + roff + e0, x0);
+      float a[8], c[8];
+      raw_unpack(g0, a); raw_unpack(x0, c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot += a[j] * c[j];
+      if (stage_row) { sg[i] = g0; sx[i] = x0; }
     }
     dot = dx_block_sum(dot, sh);
   }
@@ -93,18 +177,55 @@ __global__ void __launch_bounds__(NT) relayout_bwd_kernel(const T* __restrict__ 
     k = dot / nsq;
     if (threadIdx.x == 0 && dg) atomicAdd(dg, dot * c * inv_n);
   }
-  for (int i = threadIdx.x; i < nvec; i += NT) {
-    const int e = i << 3;
-    const int q = e / d, dd = e - q * d;
-    float gy[8];
-    dx_ld8(gdst + (((long long)b * Q + q) * P + p) * d + dd, gy);
+  if (norm && stage_row) {
+    // every thread re-reads exactly the slots it wrote: no barrier needed beyond the one inside dx_block_sum
+    for (int i = threadIdx.x; i < nvec; i += nt) {
+      float gy[8], x[8];
+      raw_unpack(sg[i], gy);
+      raw_unpack(sx[i], x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gy[j] = s * (gy[j] - x[j] * k);
+      dx_st8(dsrc + roff + (i << 3), gy);
+    }
+    return;
+  }
+  int i = threadIdx.x;
+  for (; i + nt < nvec; i += 2 * nt) {
+    Raw8<T> g0, g1, x0, x1;
+    const int e0 = i << 3, e1 = (i + nt) << 3;
+    const int q0 = e0 / d, q1 = e1 / d;
+    raw_ld(gbase + (long long)q0 * P * d + (e0 - q0 * d), g0);
+    raw_ld(gbase + (long long)q1 * P * d + (e1 - q1 * d), g1);
+    if (norm) { raw_ld(src + roff + e0, x0); raw_ld(src + roff + e1, x1); }
+    float gy[8], x[8];
+    raw_unpack(g0, gy);
     if (norm) {
-      float x[8];
-      dx_ld8(src + roff + e, x);
+      raw_unpack(x0, x);
 #pragma unroll
       for (int j = 0; j < 8; ++j) gy[j] = s * (gy[j] - x[j] * k);
     }
-    dx_st8(dsrc + roff + e, gy);
+    dx_st8(dsrc + roff + e0, gy);
+    raw_unpack(g1, gy);
+    if (norm) {
+      raw_unpack(x1, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gy[j] = s * (gy[j] - x[j] * k);
+    }
+    dx_st8(dsrc + roff + e1, gy);
+  }
+  if (i < nvec) {
+    Raw8<T> g0, x0;
+    const int e0 = i << 3, q0 = e0 / d;
+    raw_ld(gbase + (long long)q0 * P * d + (e0 - q0 * d), g0);
+    float gy[8], x[8];
+    raw_unpack(g0, gy);
+    if (norm) {
+      raw_ld(src + roff + e0, x0);
+      raw_unpack(x0, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gy[j] = s * (gy[j] - x[j] * k);
+    }
+    dx_st8(dsrc + roff + e0, gy);
   }
 }
 
@@ -206,6 +327,21 @@ __global__ void __launch_bounds__(NT) cast_kernel(const TI* __restrict__ x, TO* 
 
 }  // namespace
 
+// short rows: smaller CTAs keep more rows in flight per SM (the per-CTA latency chain load -> reduce -> store, not HBM,
+// bounds a one-row-per-CTA kernel).  DX_RELAYOUT_NT overrides.
+static int relayout_threads(int nvec, bool bwd) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("DX_RELAYOUT_NT");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 64 || forced == 128 || forced == 256) return forced;
+  // measured on B200 at the bench shapes (tools/relayout_bench.py): rows of 528 vectors: fwd 123 / 135 / 179 us and bwd
+  // 172 / 160 / 212 us with 64 / 128 / 256 threads; rows of 2064 vectors are insensitive (fwd) or best at 256 (bwd)
+  if (nvec <= 640) return bwd ? 128 : 64;
+  return 256;
+}
+
 extern "C" {
 
 int dx_relayout_fwd(const void* src, const float* src_rowsq, const float* g, const float* pos_bcast,
@@ -216,11 +352,12 @@ int dx_relayout_fwd(const void* src, const float* src_rowsq, const float* g, con
   DX_CHECK_ARG(!src_rowsq || g, "dx_relayout_fwd: src_rowsq needs g");
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = B * Q;
+  const int nt = relayout_threads((P * d) >> 3, false);
   if (act_dtype == DX_BF16)
-    relayout_fwd_kernel<bf16><<<rows, NT, 0, st>>>((const bf16*)src, src_rowsq, src_rowsq ? g : nullptr, pos_bcast,
+    relayout_fwd_kernel<bf16><<<rows, nt, 0, st>>>((const bf16*)src, src_rowsq, src_rowsq ? g : nullptr, pos_bcast,
                                                    (const bf16*)pos_batched, (bf16*)dst, dst_rowsq, B, P, Q, d);
   else
-    relayout_fwd_kernel<float><<<rows, NT, 0, st>>>((const float*)src, src_rowsq, src_rowsq ? g : nullptr, pos_bcast,
+    relayout_fwd_kernel<float><<<rows, nt, 0, st>>>((const float*)src, src_rowsq, src_rowsq ? g : nullptr, pos_bcast,
                                                     (const float*)pos_batched, (float*)dst, dst_rowsq, B, P, Q, d);
   DX_LAUNCH_CHECK();
   return DX_OK;
@@ -233,12 +370,23 @@ int dx_relayout_bwd(const void* gdst, const void* src, const float* src_rowsq, c
   DX_CHECK_ARG(!src_rowsq || (g && src), "dx_relayout_bwd: src_rowsq needs g and src");
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = B * P;
-  if (act_dtype == DX_BF16)
-    relayout_bwd_kernel<bf16><<<rows, NT, 0, st>>>((const bf16*)gdst, (const bf16*)src, src_rowsq, g, (bf16*)dsrc, dg, B,
-                                                   P, Q, d);
-  else
-    relayout_bwd_kernel<float><<<rows, NT, 0, st>>>((const float*)gdst, (const float*)src, src_rowsq, g, (float*)dsrc, dg,
-                                                    B, P, Q, d);
+  // stage the (gy, x) row in shared memory when it is short enough not to limit the CTAs per SM
+  const size_t esz = act_dtype == DX_BF16 ? 2 : 4;
+  const size_t row_bytes = 2 * (size_t)Q * d * esz;
+  const int stage_row = (src_rowsq && row_bytes <= 24 * 1024) ? 1 : 0;   // long rows: staging would cost occupancy
+  const size_t smem = stage_row ? row_bytes : 0;
+  const int nt = relayout_threads((Q * d) >> 3, true);
+  if (act_dtype == DX_BF16) {
+    auto kern = relayout_bwd_kernel<bf16>;
+    static size_t attr = 48 * 1024;
+    if (smem > attr) { DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    kern<<<rows, nt, smem, st>>>((const bf16*)gdst, (const bf16*)src, src_rowsq, g, (bf16*)dsrc, dg, B, P, Q, d, stage_row);
+  } else {
+    auto kern = relayout_bwd_kernel<float>;
+    static size_t attr = 48 * 1024;
+    if (smem > attr) { DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    kern<<<rows, nt, smem, st>>>((const float*)gdst, (const float*)src, src_rowsq, g, (float*)dsrc, dg, B, P, Q, d, stage_row);
+  }
   DX_LAUNCH_CHECK();
   return DX_OK;
 }
