@@ -220,6 +220,40 @@ def test_c1_shape_vs_oracle(mode, tol):
     _oracle_vs_cuda_student(cfg, B=4, mode=mode, tol=tol, seed=3, pool="rep_token")
 
 
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_c1_shape_ssl_step_vs_oracle(mode, tol):
+    """BASELINE.json config 3's workload (self-supervised pre-training: masked-step + masked-event reconstruction) on the
+    config-1 model shape at a reduced batch: Model.training_step(pretrain=True) incl. the host numpy-RNG masking of
+    pretrain_prep_batch (same seed -> bit-identical masks), loss and every parameter gradient against the CPU oracle."""
+    from multimodal_edema_prediction_b200.duett.duett import Model
+    cfg = O.DuettConfig(d_static_num=24, d_time_series_num=128, n_timesteps=32, d_embedding=64, n_layers=2)
+    B = 6
+    P = O.init_params(cfg, seed=11)
+    batch = O.synth_batch(cfg, B, seed=4321)
+    xs_static, xs_ts, xs_times, n_ts = O.feats_to_input(batch["x_ts"], batch["x_static"], batch["bin_ends"], cfg.T)
+    x_m, y, mask, y_ev, y_ev_mask = O.pretrain_prep_batch(np.random.default_rng(42), cfg, xs_ts, n_ts, pretrain_dropout=0.5)
+    Pl = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P.items()}
+    outs = O.model_forward_pretrain(Pl, cfg, xs_static, x_m, xs_times, training=True)
+    L_ref = O.ssl_loss(*outs, y, mask, y_ev, y_ev_mask)
+    L_ref.backward()
+    model = Model(cfg.d_static_num, cfg.V, 1, d_embedding=cfg.d_embedding, n_duett_layers=cfg.n_layers,
+                  masked_transform_timesteps=cfg.T, max_len=cfg.T, d_feedforward=cfg.d_feedforward, pretrain=True, seed=42,
+                  precision=mode)
+    model.load_state_dict(P, strict=True)
+    model.cuda().train()
+    x = (batch["x_ts"], batch["x_static"], list(batch["bin_ends"]))
+    x_pre, y2, mask2, y_ev2, y_ev_mask2 = model.pretrain_prep_batch(x, B)
+    assert torch.equal(x_pre[1].cpu(), x_m) and torch.equal(y2.cpu(), y) and torch.equal(mask2.cpu(), mask)
+    assert torch.equal(y_ev2.cpu(), y_ev) and torch.equal(y_ev_mask2.cpu(), y_ev_mask)
+    model.rng = np.random.default_rng(42)
+    loss = model.training_step((x, tuple([0.0] * B)), 0)
+    assert rel(loss.cpu(), L_ref) < tol
+    loss.backward()
+    want = {k: v.grad for k, v in Pl.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    got = _ref_keyed_grads(model)
+    _grad_check({k: got[k] for k in want}, want, tol * (1 if mode == "fp32" else 2.5), floor=5e-2)
+
+
 @pytest.mark.parametrize("mode,dauc", [("fp32", 1e-4), ("bf16", 5e-3)])
 def test_auroc_on_fixed_synthetic_eval_set(mode, dauc):
     """evaluate_binary semantics (training_duett/evaluator.py:10-37): eval-mode logits -> sigmoid -> sklearn AUROC, one
