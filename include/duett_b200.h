@@ -226,6 +226,16 @@ int dx_clip_factor(const float* sumsq, float max_norm, float* clip, void* stream
 int dx_binary_auc(const float* logits, const float* labels, int64_t n, float* key_ws, float* lab_ws, int64_t npad,
                   int apply_sigmoid, double* out, void* stream);
 
+/* ---- input binning ----------------------------------------------------------------------------------------
+ * Replaces the python row walk of duett/mimic_dataset.py:33-46 (build_stay_tensor) for a whole batch of stays in one
+ * launch.  Rows of all stays are concatenated: slot[r] = hourly slot index of row r (rows with slot >= T or < 0 are
+ * ignored by construction: no thread owns them), vals / cnts [R, V] float64 (value and observation count of every
+ * variable in that row), row_start [B+1] = first row of each stay.  x [B, T, 2V] f32 is fully written (zeros where nothing
+ * was observed); a later row of the same slot overwrites an earlier one, like the reference's sequential assignment.
+ * float64 arithmetic, one rounding to float32: bit-identical to the reference. */
+int dx_bin_events(const int* slot, const double* vals, const double* cnts, const int64_t* row_start, const double* means,
+                  const double* stds, int B, int T, int V, float* x, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

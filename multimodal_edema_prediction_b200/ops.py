@@ -423,6 +423,18 @@ def sumsq(x, out):
     _call("dx_sumsq", _p(x), x.numel(), _p(out))
 
 
+def bin_events(slot, vals, cnts, row_start, means, stds, T):
+    """Dense [B,T,2V] f32 grid from the concatenated event rows of B stays (duett/mimic_dataset.py:33-46 semantics).
+    slot [R] int32, vals / cnts [R,V] f64, row_start [B+1] int64, means / stds [V] f64 - all on the device."""
+    for t, dt in ((slot, torch.int32), (vals, torch.float64), (cnts, torch.float64), (row_start, torch.int64),
+                  (means, torch.float64), (stds, torch.float64)):
+        _chk(t, dt)
+    B, V = row_start.numel() - 1, means.numel()
+    x = torch.empty((B, T, 2 * V), device=vals.device, dtype=torch.float32)
+    _call("dx_bin_events", _p(slot), _p(vals), _p(cnts), _p(row_start), _p(means), _p(stds), B, T, V, _p(x))
+    return x
+
+
 def binary_auc(logits, labels, apply_sigmoid=True):
     """AUROC / AUPRC of a binary scorer on the device -> float64 tensor [auroc, auprc, n_pos, n] (training_duett/
     evaluator.py:22-35 semantics: sklearn roc_auc_score / average_precision_score of sigmoid(logits))."""

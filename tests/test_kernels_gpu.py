@@ -360,3 +360,41 @@ def test_sum_n(ops, dt, k):
     want = torch.stack([x.float().cpu() for x in xs]).sum(0)
     got = ops.sum_n(xs)
     assert got.dtype == dt and rel(got, want) < TOL[dt]
+
+
+def test_bin_events_bit_exact_vs_reference_golden(ops):
+    """dx_bin_events and the build_stay_tensor / build_batch_tensors mirror against the reference's own build_stay_tensor
+    (tests/golden/g5_binning.npz, oracle/make_golden_binning.py): integer/byte-level work -> bit-exact, NaN cells included."""
+    import os
+    import numpy as np
+    import pandas as pd
+    from multimodal_edema_prediction_b200.duett import mimic_dataset as md
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g5_binning.npz"))
+    T, rs = int(G["T"]), G["row_start"]
+    slot = np.where(G["slot_raw"] < 0, G["slot_raw"] + T, G["slot_raw"]).astype(np.int32)
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    x = ops.bin_events(cu(slot), cu(G["vals"]), cu(G["cnts"]), cu(rs), cu(G["means"]), cu(G["stds"]), T).cpu().numpy()
+    assert np.array_equal(x, G["x"], equal_nan=True)
+    # through the reference-facing builders, from pandas frames
+    V = G["vals"].shape[1]
+    all_vars = [f"v{j}" for j in range(V)]
+    all_counts = [f"count_v{int(k)}" for k in G["shared_count_of"]]
+    means = {v: float(m) for v, m in zip(all_vars, G["means"])}
+    stds = {v: float(s) for v, s in zip(all_vars, G["stds"])}
+    frames = []
+    for b in range(len(rs) - 1):
+        sl = slice(int(rs[b]), int(rs[b + 1]))
+        df = pd.DataFrame({"slot_idx": G["slot_raw"][sl]})
+        for j, v in enumerate(all_vars):
+            df[v] = G["vals"][sl, j]
+        for j, c in enumerate(all_counts):
+            df[c] = G["cnts"][sl, j]
+        frames.append(df)
+    xb = md.build_batch_tensors(frames, means, stds, T, all_vars, all_counts).cpu().numpy()
+    assert np.array_equal(xb, G["x"], equal_nan=True)
+    x3 = md.build_stay_tensor(frames[3], means, stds, T, all_vars, all_counts)
+    assert x3.is_cuda and np.array_equal(x3.cpu().numpy(), G["x"][3], equal_nan=True)
+    bad = frames[1].copy()
+    bad.loc[0, "slot_idx"] = -T - 1
+    with pytest.raises(IndexError):
+        md.build_stay_tensor(bad, means, stds, T, all_vars, all_counts)

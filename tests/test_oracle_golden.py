@@ -132,3 +132,15 @@ def test_ff_inner_expression():
     c = O.DuettConfig(3, 34, 24)
     assert c.ff_inner(600) == int(600 * (512 / 600)) and c.ff_inner(840) == int(840 * (512 / 840))
     assert any(int(dim * (512 / dim)) == 511 for dim in range(8, 4000, 8))
+
+
+def test_binning_oracle_matches_reference_golden():
+    """oracle/binning_oracle.py against the output of the reference's own build_stay_tensor (duett/mimic_dataset.py:33-46)
+    on 7 synthetic stays: bit-exact, NaN cells included."""
+    import os
+    import numpy as np
+    from oracle import binning_oracle
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g5_binning.npz"))
+    x = binning_oracle.bin_events(G["slot_raw"], G["vals"], G["cnts"], G["row_start"], G["means"], G["stds"], int(G["T"]))
+    assert x.dtype == np.float32 and x.shape == G["x"].shape
+    assert np.array_equal(x, G["x"], equal_nan=True)
