@@ -124,18 +124,23 @@ int dx_rowdot_scale(const void* a, void* g, const float* row_scale, float* rowdo
 /* sink[0] += sum(x)/g[0]: ScaleNorm gain gradient. */
 int dx_sum_div_acc(const float* x, int64_t n, const float* g, float* sink, void* stream);
 
-/* Unmasked multi-head attention core softmax(q k^T / sqrt(dh)) v, fp32 softmax.  Element (b,s,h,i) of a tensor lives at
- * ptr + b*bs + s*rs + h*dh + i (strides in elements).  lse: [B,H,Sq] f32.  dh in {4,8,12,16,32,64,128}.
+/* Unmasked multi-head attention core dropout(softmax(q k^T / sqrt(dh))) v, fp32 softmax.  Element (b,s,h,i) of a tensor
+ * lives at ptr + b*bs + s*rs + h*dh + i (strides in elements).  lse: [B,H,Sq] f32.  dh in {4,8,12,16,32,64,128}.
+ * Dropout on the attention probabilities (attn_dropout of the x_transformers Encoder, duett/duett.py:98,104; dropout of
+ * nn.MultiheadAttention in _PerceiverBlock): drop_p in [0,1); probability (b,h,q,k) is kept iff
+ * splitmix64(seed + idx * 0x9E3779B97F4A7C15) >> 32 >= drop_p * 2^32 with idx = ((b*H+h)*Sq+q)*Sk+k and
+ * seed = drop_seed + (drop_seed_dev ? *drop_seed_dev : 0), and scaled by 1/(1-drop_p); the backward call regenerates the
+ * mask from the same (drop_p, seed).  drop_p = 0 disables it.
  * Replaces: x_transformers Attention core (duett/duett.py:95-105 call sites :276,:279) and the nn.MultiheadAttention core
  * of _PerceiverBlock (models/main_architecture_duett.py:752,759). */
 int dx_attn_fwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_rs, const void* v,
                 int64_t v_bs, int64_t v_rs, void* o, int64_t o_bs, int64_t o_rs, float* lse, int B, int H, int Sq, int Sk,
-                int dh, int dtype, void* stream);
+                int dh, int dtype, float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_dev, void* stream);
 int dx_attn_bwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_rs, const void* v,
                 int64_t v_bs, int64_t v_rs, const void* o, int64_t o_bs, int64_t o_rs, const void* go, int64_t go_bs,
                 int64_t go_rs, void* dq, int64_t dq_bs, int64_t dq_rs, void* dk, int64_t dk_bs, int64_t dk_rs, void* dv,
                 int64_t dv_bs, int64_t dv_rs, const float* lse, float* D_ws, int B, int H, int Sq, int Sk, int dh,
-                int dtype, void* stream);
+                int dtype, float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_dev, void* stream);
 
 /* Value/count embedding into psi[B,T+1,V+1,d] (duett/duett.py:245-266 == models/main_architecture_duett.py:31-65, the
  * per-variable Python loop): count lookup (n_obs_embedding, clip 0..15), V grouped MLPs
@@ -216,6 +221,14 @@ int dx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, 
              const float* lr_scale_dev, void* stream);
 int dx_sumsq(const float* x, int64_t n, float* out, void* stream);
 int dx_clip_factor(const float* sumsq, float max_norm, float* clip, void* stream);
+
+/* nn.Dropout (heads, perceiver feed-forward, FFN hidden of the axis encoders: ff_dropout, duett/duett.py:99,105):
+ * y[i] = x[i] * keep(i) / (1-p) with the generator of dx_attn_fwd over the flat index i; applying the same call to the
+ * upstream gradient is the backward pass.  x == y allowed. */
+int dx_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, int dtype, void* stream);
+/* out[n] = sum_c a[n,c] * (b[n,c] - bias[c])  (bias may be NULL): the FFN ScaleNorm-backward row dot when a dropout mask
+ * sits between the GELU and W2 (the fused GELU' epilogue of dx_gemm computes it only for the mask-free case). */
+int dx_rowdot_bias(const void* a, const void* b, const float* bias, float* out, int N, int C, int dtype, void* stream);
 
 /* ---- evaluation metrics --------------------------------------------------------------------------------
  * Replaces the host-side scoring of training_duett/evaluator.py:22-35 (torch.sigmoid -> .numpy() -> sklearn

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-P, I, L, F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+P, I, L, F, U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 
 SIGNATURES = {
     # name: argtypes (the trailing P is always the cudaStream_t)
@@ -12,8 +12,10 @@ SIGNATURES = {
     "dx_colsum": [P, L, I, L, P, I, I, P],
     "dx_axpy": [P, P, L, F, I, I, P],
     "dx_cast": [P, I, P, I, L, P],
-    "dx_attn_fwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, I, I, I, I, I, I, P],
-    "dx_attn_bwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, P, I, I, I, I, I, I, P],
+    "dx_attn_fwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, I, I, I, I, I, I, F, U64, P, P],
+    "dx_attn_bwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, P, I, I, I, I, I, I, F, U64, P, P],
+    "dx_dropout": [P, P, L, F, U64, P, I, P],
+    "dx_rowdot_bias": [P, P, P, P, I, I, I, P],
     "dx_rowdot_scale": [P, P, P, P, I, I, I, P],
     "dx_scalenorm_scale": [P, P, F, P, I, P],
     "dx_embed_stats": [P, I, I, I, P, P, P, P, P, P, P, P, I, P],

@@ -35,10 +35,10 @@ GRAD_READY_HOOK = None
 class EncoderCtx:
     """Saved activations of one Encoder forward."""
     __slots__ = ("x", "rowsq_x", "s_a", "qkv", "o", "lse", "x1", "rowsq1", "s_f", "fpre", "h", "x2", "rowsq2", "B", "S",
-                 "dim")
+                 "dim", "drop_attn", "drop_ff")
 
 
-def encoder_fwd(x, rowsq_x, B, S, dim, p, heads, d, keep=True):
+def encoder_fwd(x, rowsq_x, B, S, dim, p, heads, d, keep=True, drop_p=0.0, tag=""):
     """x: [B,S,dim] act tensor (dense), rowsq_x [B*S]. p: dict ENC_KEYS -> tensors (weights already in act dtype under
     'wqkv_c','wo_c','w1_c','w2_c'). Returns ctx with x2 / rowsq2 (un-normalised output + row norms)."""
     N = B * S
@@ -49,7 +49,11 @@ def encoder_fwd(x, rowsq_x, B, S, dim, p, heads, d, keep=True):
     qkv = torch.empty((N, 3 * d), device=dev, dtype=at)
     ops.gemm_(x2d, p["wqkv_c"], out=qkv, row_scale=s_a, act_dtype=at)
     q3 = qkv.view(B, S, 3 * d)
-    o, lse = ops.attn_fwd(q3[:, :, :d], q3[:, :, d:2 * d], q3[:, :, 2 * d:], heads)
+    # attn_dropout / ff_dropout of the x_transformers Encoder (duett/duett.py:98-99,104-105): on the attention probabilities
+    # and on the FFN hidden after the GELU
+    drop_attn = (drop_p, ops.drop_seed(tag + ".attn", drop_p, (B, heads, S, S))) if drop_p > 0 else None
+    drop_ff = (drop_p, ops.drop_seed(tag + ".ff", drop_p, (N, F))) if drop_p > 0 else None
+    o, lse = ops.attn_fwd(q3[:, :, :d], q3[:, :, d:2 * d], q3[:, :, 2 * d:], heads, drop_attn)
     x1 = torch.empty((N, dim), device=dev, dtype=at)
     rowsq1 = torch.zeros(N, device=dev, dtype=torch.float32)
     ops.gemm_(o.view(N, d), p["wo_c"], out=x1, res=x2d, row_sumsq=rowsq1, act_dtype=at)
@@ -57,6 +61,8 @@ def encoder_fwd(x, rowsq_x, B, S, dim, p, heads, d, keep=True):
     h = torch.empty((N, F), device=dev, dtype=at)
     fpre = torch.empty((N, F), device=dev, dtype=at)
     ops.gemm_(x1, p["w1_c"], out=h, out2=fpre, row_scale=s_f, bias=p["b1"], act=ops.ACT_GELU, act_dtype=at)
+    if drop_ff:
+        ops.dropout(h, drop_ff[0], drop_ff[1], out=h)       # in place: the saved h is the dropped one (dW2 needs that)
     x2 = torch.empty((N, dim), device=dev, dtype=at)
     rowsq2 = torch.zeros(N, device=dev, dtype=torch.float32)
     ops.gemm_(h, p["w2_c"], out=x2, bias=p["b2"], res=x1, row_sumsq=rowsq2, act_dtype=at)
@@ -64,6 +70,7 @@ def encoder_fwd(x, rowsq_x, B, S, dim, p, heads, d, keep=True):
     c.x, c.rowsq_x, c.s_a, c.qkv, c.o, c.lse = x2d, rowsq_x, s_a, qkv, o, lse
     c.x1, c.rowsq1, c.s_f, c.fpre, c.h, c.x2, c.rowsq2 = x1, rowsq1, s_f, fpre, h, x2, rowsq2
     c.B, c.S, c.dim = B, S, dim
+    c.drop_attn, c.drop_ff = drop_attn, drop_ff
     return c
 
 
@@ -84,6 +91,12 @@ def encoder_bwd(c: EncoderCtx, dx2, p, G, heads, d):
     df = torch.empty((N, F), device=dev, dtype=at)       # dpre
     ops.gemm_(dx2, p["w2_c"], b_mn=True, out=dfs, out2=df, act=ops.ACT_GELU_BWD, aux=c.fpre, aux_bias=p["b1"],
               row_scale2=c.s_f, row_dot=rowdot_f, act_dtype=at)                                # dh = dx2 W2, through GELU'
+    if c.drop_ff:
+        # dpre = (dx2 W2) * mask/(1-p) * GELU'(pre): the mask commutes with the element-wise GELU' factor, so it is applied
+        # to the epilogue's outputs; the row dot <dpre, pre - b1> has to be taken after it
+        ops.dropout(df, c.drop_ff[0], c.drop_ff[1], out=df)
+        ops.dropout(dfs, c.drop_ff[0], c.drop_ff[1], out=dfs)
+        rowdot_f = ops.rowdot_bias(df, c.fpre, p["b1"])
     if "b1" in G:
         ops.colsum(df, G["b1"], accumulate=True)
     if "w1" in G:
@@ -100,7 +113,7 @@ def encoder_bwd(c: EncoderCtx, dx2, p, G, heads, d):
     dqkv = torch.empty((N, 3 * d), device=dev, dtype=at)
     q3, g3 = c.qkv.view(B, S, 3 * d), dqkv.view(B, S, 3 * d)
     ops.attn_bwd(q3[:, :, :d], q3[:, :, d:2 * d], q3[:, :, 2 * d:], c.o, do.view(B, S, d), c.lse, heads,
-                 g3[:, :, :d], g3[:, :, d:2 * d], g3[:, :, 2 * d:])
+                 g3[:, :, :d], g3[:, :, d:2 * d], g3[:, :, 2 * d:], c.drop_attn)
     rowdot_a = ops.rowdot_scale(c.qkv, dqkv, c.s_a)      # dqkv <- s_a * dqkv in place
     if "g_attn" in G:
         _acc_g(G["g_attn"], rowdot_a, p["g_attn"])
@@ -141,12 +154,13 @@ class DuettEncodeFn(torch.autograd.Function):
             pe = _enc_params(det, f"event_transformers.{l}", at)
             x_e, rsq = ops.relayout_fwd(src, B, T1, V1, cfgd, src_rowsq=src_rowsq, g=g_prev,
                                         pos_bcast=det["full_event_embedding.weight"])
-            ce = encoder_fwd(x_e.view(B, V1, E), rsq, B, V1, E, pe, heads, cfgd)
+            dp = float(spec.get("dropout", 0.0)) if training else 0.0
+            ce = encoder_fwd(x_e.view(B, V1, E), rsq, B, V1, E, pe, heads, cfgd, drop_p=dp, tag=f"event_transformers.{l}")
             pt = _enc_params(det, f"time_transformers.{l}", at)
             x_t, rsq = ops.relayout_fwd(ce.x2.view(B, V1, T1, cfgd), B, V1, T1, cfgd,
                                         src_rowsq=ce.rowsq2 if spec["final_norm"] else None, g=pe["g_final"],
                                         pos_batched=te.detach())
-            ct = encoder_fwd(x_t.view(B, T1, Ep), rsq, B, T1, Ep, pt, heads, cfgd)
+            ct = encoder_fwd(x_t.view(B, T1, Ep), rsq, B, T1, Ep, pt, heads, cfgd, drop_p=dp, tag=f"time_transformers.{l}")
             encs.append((ce, ct))
             src, src_rowsq, g_prev = ct.x2.view(B, T1, V1, cfgd), (ct.rowsq2 if spec["final_norm"] else None), pt["g_final"]
         out, _ = ops.relayout_fwd(src.view(B * T1, 1, 1, Ep), B * T1, 1, 1, Ep, src_rowsq=src_rowsq, g=g_prev,

@@ -15,12 +15,12 @@
 bool dx_attn_mma_supported(const void* const* ptrs, const long long* bs, const long long* rs, int n, int Sq, int Sk, int dh);
 int dx_attn_mma_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
                     long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse, int B, int H, int Sq,
-                    int Sk, int dh, cudaStream_t st);
+                    int Sk, int dh, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st);
 int dx_attn_mma_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
                     long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs, const void* go, long long go_bs,
                     long long go_rs, void* dq, long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs,
                     void* dv, long long dv_bs, long long dv_rs, const float* lse, int B, int H, int Sq, int Sk, int dh,
-                    cudaStream_t st);
+                    DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st);
 
 namespace {
 
@@ -91,7 +91,9 @@ __device__ __forceinline__ void axpy4(float (&acc)[DHT], float p, const float* _
 
 template <typename T, int DH, int TPQ>
 __global__ void __launch_bounds__(NTH) attn_fwd_kernel(AttnView q, AttnView k, AttnView v, AttnViewW o, float* lse,
-                                                      int H, int Sq, int Sk, float scale) {
+                                                      int H, int Sq, int Sk, float scale, DxDrop drop,
+                                                      const unsigned long long* seed_dev) {
+  drop = dx_drop_resolve(drop, seed_dev);
   constexpr int DHT = DH / TPQ;
   extern __shared__ __align__(16) float smem[];
   float* sk = smem;
@@ -107,6 +109,7 @@ __global__ void __launch_bounds__(NTH) attn_fwd_kernel(AttnView q, AttnView k, A
     acc[i] = 0.f;
   }
   float m = -INFINITY, l = 0.f;
+  const unsigned long long drow = ((unsigned long long)blockIdx.x * Sq + (unsigned)qi) * (unsigned long long)Sk;   // (b*H+h, q) row
   for (int k0 = 0; k0 < Sk; k0 += KT) {
     __syncthreads();
     load_tile<T, DH>(sk, k, b, h, k0, Sk);
@@ -126,8 +129,9 @@ __global__ void __launch_bounds__(NTH) attn_fwd_kernel(AttnView q, AttnView k, A
         m = s;
       }
       const float p = __expf(s - m);
-      l += p;
-      axpy4<DHT>(acc, p, sv + j * DH + part * DHT);
+      l += p;   // softmax normaliser: before dropout
+      const float pd = drop.thresh ? p * dx_drop_factor(drop, drow + (unsigned)(k0 + j)) : p;
+      axpy4<DHT>(acc, pd, sv + j * DH + part * DHT);
     }
   }
   if (active) {
@@ -143,7 +147,8 @@ __global__ void __launch_bounds__(NTH) attn_fwd_kernel(AttnView q, AttnView k, A
 template <typename T, int DH, int TPQ>
 __global__ void __launch_bounds__(NTH) attn_bwd_q_kernel(AttnView q, AttnView k, AttnView v, AttnView o, AttnView go,
                                                         AttnViewW dq, const float* lse, float* Dv, int H, int Sq, int Sk,
-                                                        float scale) {
+                                                        float scale, DxDrop drop, const unsigned long long* seed_dev) {
+  drop = dx_drop_resolve(drop, seed_dev);
   constexpr int DHT = DH / TPQ;
   extern __shared__ __align__(16) float smem[];
   float* sk = smem;
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(NTH) attn_bwd_q_kernel(AttnView q, AttnView k,
 #pragma unroll
   for (int off = 1; off < TPQ; off <<= 1) D += __shfl_xor_sync(0xffffffffu, D, off);
   const float L = active ? lse[((long long)b * H + h) * Sq + qi] : 0.f;
+  const unsigned long long drow = ((unsigned long long)blockIdx.x * Sq + (unsigned)qi) * (unsigned long long)Sk;
   for (int k0 = 0; k0 < Sk; k0 += KT) {
     __syncthreads();
     load_tile<T, DH>(sk, k, b, h, k0, Sk);
@@ -181,6 +187,7 @@ __global__ void __launch_bounds__(NTH) attn_bwd_q_kernel(AttnView q, AttnView k,
         s += __shfl_xor_sync(0xffffffffu, s, off);
         dp += __shfl_xor_sync(0xffffffffu, dp, off);
       }
+      if (drop.thresh) dp *= dx_drop_factor(drop, drow + (unsigned)(k0 + j));   // dP = dP_dropped * mask / (1-p)
       const float ds = __expf(s - L) * (dp - D);
       axpy4<DHT>(acc, ds, kj);
     }
@@ -197,7 +204,8 @@ __global__ void __launch_bounds__(NTH) attn_bwd_q_kernel(AttnView q, AttnView k,
 template <typename T, int DH, int TPQ>
 __global__ void __launch_bounds__(NTH) attn_bwd_kv_kernel(AttnView q, AttnView k, AttnView v, AttnView go, AttnViewW dk,
                                                          AttnViewW dv, const float* lse, const float* Dv, int H, int Sq,
-                                                         int Sk, float scale) {
+                                                         int Sk, float scale, DxDrop drop, const unsigned long long* seed_dev) {
+  drop = dx_drop_resolve(drop, seed_dev);
   constexpr int DHT = DH / TPQ;
   extern __shared__ __align__(16) float smem[];
   float* sq = smem;
@@ -238,8 +246,11 @@ __global__ void __launch_bounds__(NTH) attn_bwd_kv_kernel(AttnView q, AttnView k
         dp += __shfl_xor_sync(0xffffffffu, dp, off);
       }
       const float p = __expf(s * scale - sl[i2]);
-      const float ds = p * (dp - sd[i2]);
-      axpy4<DHT>(av, p, gi);
+      const float mk = drop.thresh
+                           ? dx_drop_factor(drop, ((unsigned long long)blockIdx.x * Sq + (unsigned)(q0 + i2)) * (unsigned long long)Sk + (unsigned)kj)
+                           : 1.f;
+      const float ds = p * (dp * mk - sd[i2]);
+      axpy4<DHT>(av, p * mk, gi);
       axpy4<DHT>(ak, ds, qi);
     }
   }
@@ -283,12 +294,12 @@ __global__ void scalenorm_scale_kernel(const float* __restrict__ rowsq, const fl
 
 template <typename T, int DH, int TPQ>
 int launch_fwd(const AttnView& q, const AttnView& k, const AttnView& v, const AttnViewW& o, float* lse, int B, int H,
-               int Sq, int Sk, float scale, cudaStream_t st) {
+               int Sq, int Sk, float scale, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st) {
   const size_t smem = 2 * KT * DH * sizeof(float);
   auto kern = attn_fwd_kernel<T, DH, TPQ>;
   if (smem > 48 * 1024) DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(B * H, dx_ceil_div(Sq, NTH / TPQ));
-  kern<<<grid, NTH, smem, st>>>(q, k, v, o, lse, H, Sq, Sk, scale);
+  kern<<<grid, NTH, smem, st>>>(q, k, v, o, lse, H, Sq, Sk, scale, drop, seed_dev);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }
@@ -296,7 +307,7 @@ int launch_fwd(const AttnView& q, const AttnView& k, const AttnView& v, const At
 template <typename T, int DH, int TPQ>
 int launch_bwd(const AttnView& q, const AttnView& k, const AttnView& v, const AttnView& o, const AttnView& go,
                const AttnViewW& dq, const AttnViewW& dk, const AttnViewW& dv, const float* lse, float* Dv, int B, int H,
-               int Sq, int Sk, float scale, cudaStream_t st) {
+               int Sq, int Sk, float scale, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st) {
   const size_t smem_q = 2 * KT * DH * sizeof(float);
   const size_t smem_kv = (2 * KT * DH + 2 * KT) * sizeof(float);
   auto kq = attn_bwd_q_kernel<T, DH, TPQ>;
@@ -306,10 +317,10 @@ int launch_bwd(const AttnView& q, const AttnView& k, const AttnView& v, const At
     DX_CUDA(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
   }
   dim3 gq(B * H, dx_ceil_div(Sq, NTH / TPQ));
-  kq<<<gq, NTH, smem_q, st>>>(q, k, v, o, go, dq, lse, Dv, H, Sq, Sk, scale);
+  kq<<<gq, NTH, smem_q, st>>>(q, k, v, o, go, dq, lse, Dv, H, Sq, Sk, scale, drop, seed_dev);
   DX_LAUNCH_CHECK();
   dim3 gk(B * H, dx_ceil_div(Sk, NTH / TPQ));
-  kkv<<<gk, NTH, smem_kv, st>>>(q, k, v, go, dk, dv, lse, Dv, H, Sq, Sk, scale);
+  kkv<<<gk, NTH, smem_kv, st>>>(q, k, v, go, dk, dv, lse, Dv, H, Sq, Sk, scale, drop, seed_dev);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }
@@ -335,19 +346,22 @@ extern "C" {
 /* q/k/v/o: element (b,s,h,i) at ptr + b*bs + s*rs + h*dh + i (strides in elements). */
 int dx_attn_fwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_rs, const void* v,
                 int64_t v_bs, int64_t v_rs, void* o, int64_t o_bs, int64_t o_rs, float* lse, int B, int H, int Sq, int Sk,
-                int dh, int dtype, void* stream) {
+                int dh, int dtype, float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_dev, void* stream) {
   DX_CHECK_ARG(q && k && v && o, "dx_attn_fwd: null tensor");
+  DX_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "dx_attn_fwd: dropout probability must be in [0, 1)");
   cudaStream_t st = (cudaStream_t)stream;
+  const DxDrop drop = dx_make_drop(drop_p, drop_seed);
+  const unsigned long long* seed_dev = reinterpret_cast<const unsigned long long*>(drop_seed_dev);
   if (dtype == DX_BF16 && !attn_force_simt()) {
     const void* ptrs[4] = {q, k, v, o};
     const long long bs[4] = {q_bs, k_bs, v_bs, o_bs}, rs[4] = {q_rs, k_rs, v_rs, o_rs};
     if (dx_attn_mma_supported(ptrs, bs, rs, 4, Sq, Sk, dh))
-      return dx_attn_mma_fwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, B, H, Sq, Sk, dh, st);
+      return dx_attn_mma_fwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, B, H, Sq, Sk, dh, drop, seed_dev, st);
   }
   AttnView Q{q, q_bs, q_rs}, K{k, k_bs, k_rs}, V{v, v_bs, v_rs};
   AttnViewW O{o, o_bs, o_rs};
   const float scale = 1.f / sqrtf((float)dh);
-#define CALL_FWD(T, DH, TPQ) launch_fwd<T, DH, TPQ>(Q, K, V, O, lse, B, H, Sq, Sk, scale, st)
+#define CALL_FWD(T, DH, TPQ) launch_fwd<T, DH, TPQ>(Q, K, V, O, lse, B, H, Sq, Sk, scale, drop, seed_dev, st)
   if (dtype == DX_BF16) { DX_ATTN_DISPATCH(bf16, CALL_FWD) } else { DX_ATTN_DISPATCH(float, CALL_FWD) }
 #undef CALL_FWD
 }
@@ -356,21 +370,24 @@ int dx_attn_bwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_
                 int64_t v_bs, int64_t v_rs, const void* o, int64_t o_bs, int64_t o_rs, const void* go, int64_t go_bs,
                 int64_t go_rs, void* dq, int64_t dq_bs, int64_t dq_rs, void* dk, int64_t dk_bs, int64_t dk_rs, void* dv,
                 int64_t dv_bs, int64_t dv_rs, const float* lse, float* D_ws, int B, int H, int Sq, int Sk, int dh,
-                int dtype, void* stream) {
+                int dtype, float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_dev, void* stream) {
   DX_CHECK_ARG(q && k && v && o && go && dq && dk && dv && lse && D_ws, "dx_attn_bwd: null tensor");
+  DX_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "dx_attn_bwd: dropout probability must be in [0, 1)");
   cudaStream_t st = (cudaStream_t)stream;
+  const DxDrop drop = dx_make_drop(drop_p, drop_seed);
+  const unsigned long long* seed_dev = reinterpret_cast<const unsigned long long*>(drop_seed_dev);
   if (dtype == DX_BF16 && !attn_force_simt()) {
     const void* ptrs[8] = {q, k, v, o, go, dq, dk, dv};
     const long long bs[8] = {q_bs, k_bs, v_bs, o_bs, go_bs, dq_bs, dk_bs, dv_bs};
     const long long rs[8] = {q_rs, k_rs, v_rs, o_rs, go_rs, dq_rs, dk_rs, dv_rs};
     if (dx_attn_mma_supported(ptrs, bs, rs, 8, Sq, Sk, dh))
       return dx_attn_mma_bwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, go, go_bs, go_rs, dq, dq_bs, dq_rs, dk,
-                             dk_bs, dk_rs, dv, dv_bs, dv_rs, lse, B, H, Sq, Sk, dh, st);
+                             dk_bs, dk_rs, dv, dv_bs, dv_rs, lse, B, H, Sq, Sk, dh, drop, seed_dev, st);
   }
   AttnView Q{q, q_bs, q_rs}, K{k, k_bs, k_rs}, V{v, v_bs, v_rs}, O{o, o_bs, o_rs}, GO{go, go_bs, go_rs};
   AttnViewW DQ{dq, dq_bs, dq_rs}, DK{dk, dk_bs, dk_rs}, DV{dv, dv_bs, dv_rs};
   const float scale = 1.f / sqrtf((float)dh);
-#define CALL_BWD(T, DH, TPQ) launch_bwd<T, DH, TPQ>(Q, K, V, O, GO, DQ, DK, DV, lse, D_ws, B, H, Sq, Sk, scale, st)
+#define CALL_BWD(T, DH, TPQ) launch_bwd<T, DH, TPQ>(Q, K, V, O, GO, DQ, DK, DV, lse, D_ws, B, H, Sq, Sk, scale, drop, seed_dev, st)
   if (dtype == DX_BF16) { DX_ATTN_DISPATCH(bf16, CALL_BWD) } else { DX_ATTN_DISPATCH(float, CALL_BWD) }
 #undef CALL_BWD
 }

@@ -120,7 +120,9 @@ __device__ __forceinline__ void store_frag(const ViewW& o, int b, int h, int m0,
 
 template <int DH>
 __global__ void __launch_bounds__(288) attn_mma_fwd_kernel(View q, View k, View v, ViewW o, float* __restrict__ lse, int H,
-                                                          int Sq, int Sk, float scale) {
+                                                          int Sq, int Sk, float scale, DxDrop drop,
+                                                          const unsigned long long* __restrict__ seed_dev) {
+  drop = dx_drop_resolve(drop, seed_dev);
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int SPq = (Sq + 15) & ~15, SPk = (Sk + 15) & ~15;
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(288) attn_mma_fwd_kernel(View q, View k, View 
   for (int i = 0; i < DH / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
   float mx[2] = {-INFINITY, -INFINITY}, ls[2] = {0.f, 0.f};   // running row max (log2 domain) / thread-partial row sums
   const float sc2 = scale * LOG2E;
+  const unsigned long long dbase = (unsigned long long)blockIdx.x * Sq;   // (b*H + h) * Sq
   for (int k0 = 0; k0 < SPk; k0 += 16) {
     float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     mma_a_xt<DH>(s, qa, uK, k0, lane);
@@ -161,9 +164,16 @@ __global__ void __launch_bounds__(288) attn_mma_fwd_kernel(View q, View k, View 
       const float mnew = fmaxf(mx[r], m);       // finite: key block 0 always holds a valid key
       const float corr = ex2(mx[r] - mnew);
       mx[r] = mnew;
-      const float p00 = ex2(s[0][2 * r] - mnew), p01 = ex2(s[0][2 * r + 1] - mnew);
-      const float p10 = ex2(s[1][2 * r] - mnew), p11 = ex2(s[1][2 * r + 1] - mnew);
-      ls[r] = ls[r] * corr + (p00 + p01) + (p10 + p11);
+      float p00 = ex2(s[0][2 * r] - mnew), p01 = ex2(s[0][2 * r + 1] - mnew);
+      float p10 = ex2(s[1][2 * r] - mnew), p11 = ex2(s[1][2 * r + 1] - mnew);
+      ls[r] = ls[r] * corr + (p00 + p01) + (p10 + p11);   // softmax normaliser: before dropout
+      if (drop.thresh) {
+        const unsigned long long di = (dbase + (unsigned)(m0 + (lane >> 2) + 8 * r)) * (unsigned long long)Sk + (unsigned)(k0 + 2 * t);
+        p00 *= dx_drop_factor(drop, di);
+        p01 *= dx_drop_factor(drop, di + 1);
+        p10 *= dx_drop_factor(drop, di + 8);
+        p11 *= dx_drop_factor(drop, di + 9);
+      }
 #pragma unroll
       for (int i = 0; i < DH / 8; ++i) {
         acc[i][2 * r] *= corr;
@@ -190,7 +200,10 @@ __global__ void __launch_bounds__(288) attn_mma_fwd_kernel(View q, View k, View 
 
 template <int DH>
 __global__ void __launch_bounds__(288) attn_mma_bwd_kernel(View q, View k, View v, View o, View go, ViewW dq, ViewW dk, ViewW dv,
-                                                          const float* __restrict__ lse, int H, int Sq, int Sk, float scale) {
+                                                          const float* __restrict__ lse, int H, int Sq, int Sk, float scale,
+                                                          DxDrop drop, const unsigned long long* __restrict__ seed_dev) {
+  drop = dx_drop_resolve(drop, seed_dev);
+  const unsigned long long dbase = (unsigned long long)blockIdx.x * Sq;   // (b*H + h) * Sq
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int SPq = (Sq + 15) & ~15, SPk = (Sk + 15) & ~15;
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
@@ -246,7 +259,10 @@ __global__ void __launch_bounds__(288) attn_mma_bwd_kernel(View q, View k, View 
         for (int e = 0; e < 4; ++e) {
           const int key = k0 + nt * 8 + 2 * t + (e & 1);
           const float p = key < Sk ? ex2(s[nt][e] * sc2 - L[e >> 1]) : 0.f;
-          ds[nt][e] = p * (dp[nt][e] - Dr[e >> 1]);
+          float dpe = dp[nt][e];
+          if (drop.thresh)
+            dpe *= dx_drop_factor(drop, (dbase + (unsigned)(m0 + g + 8 * (e >> 1))) * (unsigned long long)Sk + (unsigned)key);
+          ds[nt][e] = p * (dpe - Dr[e >> 1]);
         }
       const uint32_t dsa[4] = {pack2(ds[0][0], ds[0][1]), pack2(ds[0][2], ds[0][3]), pack2(ds[1][0], ds[1][1]),
                                pack2(ds[1][2], ds[1][3])};
@@ -275,8 +291,12 @@ __global__ void __launch_bounds__(288) attn_mma_bwd_kernel(View q, View k, View 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int qi = q0 + nt * 8 + 2 * t + (e & 1);
-          p[nt][e] = qi < Sq ? ex2(s[nt][e] * sc2 - sL[qi]) : 0.f;
-          ds[nt][e] = p[nt][e] * (dp[nt][e] - sD[qi]);
+          const float pe = qi < Sq ? ex2(s[nt][e] * sc2 - sL[qi]) : 0.f;
+          const float mk = drop.thresh
+                               ? dx_drop_factor(drop, (dbase + (unsigned)qi) * (unsigned long long)Sk + (unsigned)(m0 + g + 8 * (e >> 1)))
+                               : 1.f;
+          ds[nt][e] = pe * (dp[nt][e] * mk - sD[qi]);
+          p[nt][e] = pe * mk;   // dV uses the dropped probabilities
         }
       const uint32_t pa[4] = {pack2(p[0][0], p[0][1]), pack2(p[0][2], p[0][3]), pack2(p[1][0], p[1][1]), pack2(p[1][2], p[1][3])};
       const uint32_t dsa[4] = {pack2(ds[0][0], ds[0][1]), pack2(ds[0][2], ds[0][3]), pack2(ds[1][0], ds[1][1]),
@@ -295,7 +315,7 @@ inline bool view_ok(const void* p, long long bs, long long rs, int dh) {
 
 template <int DH>
 int launch_fwd(const View& q, const View& k, const View& v, const ViewW& o, float* lse, int B, int H, int Sq, int Sk,
-               float scale, cudaStream_t st) {
+               float scale, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st) {
   const int SPq = (Sq + 15) & ~15, SPk = (Sk + 15) & ~15;
   const size_t smem = (size_t)(SPq + 2 * SPk) * (DH + PAD) * 2;
   auto kern = attn_mma_fwd_kernel<DH>;
@@ -305,14 +325,15 @@ int launch_fwd(const View& q, const View& k, const View& v, const ViewW& o, floa
     attr = smem;
   }
   const int nw = (SPq > SPk ? SPq : SPk) / 16;
-  kern<<<B * H, 32 * nw, smem, st>>>(q, k, v, o, lse, H, Sq, Sk, scale);
+  kern<<<B * H, 32 * nw, smem, st>>>(q, k, v, o, lse, H, Sq, Sk, scale, drop, seed_dev);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }
 
 template <int DH>
 int launch_bwd(const View& q, const View& k, const View& v, const View& o, const View& go, const ViewW& dq, const ViewW& dk,
-               const ViewW& dv, const float* lse, int B, int H, int Sq, int Sk, float scale, cudaStream_t st) {
+               const ViewW& dv, const float* lse, int B, int H, int Sq, int Sk, float scale, DxDrop drop,
+               const unsigned long long* seed_dev, cudaStream_t st) {
   const int SPq = (Sq + 15) & ~15, SPk = (Sk + 15) & ~15;
   const size_t smem = (size_t)(2 * SPq + 2 * SPk) * (DH + PAD) * 2 + 2 * SPq * sizeof(float);
   auto kern = attn_mma_bwd_kernel<DH>;
@@ -322,7 +343,7 @@ int launch_bwd(const View& q, const View& k, const View& v, const View& o, const
     attr = smem;
   }
   const int nw = (SPq > SPk ? SPq : SPk) / 16;
-  kern<<<B * H, 32 * nw, smem, st>>>(q, k, v, o, go, dq, dk, dv, lse, H, Sq, Sk, scale);
+  kern<<<B * H, 32 * nw, smem, st>>>(q, k, v, o, go, dq, dk, dv, lse, H, Sq, Sk, scale, drop, seed_dev);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }
@@ -341,15 +362,15 @@ bool dx_attn_mma_supported(const void* const* ptrs, const long long* bs, const l
 
 int dx_attn_mma_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
                     long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse, int B, int H, int Sq,
-                    int Sk, int dh, cudaStream_t st) {
+                    int Sk, int dh, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st) {
   using namespace dx_attn_mma;
   View Q{(const bf16*)q, q_bs, q_rs}, K{(const bf16*)k, k_bs, k_rs}, V{(const bf16*)v, v_bs, v_rs};
   ViewW O{(bf16*)o, o_bs, o_rs};
   const float scale = 1.f / sqrtf((float)dh);
   switch (dh) {
-    case 16: return launch_fwd<16>(Q, K, V, O, lse, B, H, Sq, Sk, scale, st);
-    case 32: return launch_fwd<32>(Q, K, V, O, lse, B, H, Sq, Sk, scale, st);
-    default: return launch_fwd<64>(Q, K, V, O, lse, B, H, Sq, Sk, scale, st);
+    case 16: return launch_fwd<16>(Q, K, V, O, lse, B, H, Sq, Sk, scale, drop, seed_dev, st);
+    case 32: return launch_fwd<32>(Q, K, V, O, lse, B, H, Sq, Sk, scale, drop, seed_dev, st);
+    default: return launch_fwd<64>(Q, K, V, O, lse, B, H, Sq, Sk, scale, drop, seed_dev, st);
   }
 }
 
@@ -357,15 +378,15 @@ int dx_attn_mma_bwd(const void* q, long long q_bs, long long q_rs, const void* k
                     long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs, const void* go, long long go_bs,
                     long long go_rs, void* dq, long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs,
                     void* dv, long long dv_bs, long long dv_rs, const float* lse, int B, int H, int Sq, int Sk, int dh,
-                    cudaStream_t st) {
+                    DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st) {
   using namespace dx_attn_mma;
   View Q{(const bf16*)q, q_bs, q_rs}, K{(const bf16*)k, k_bs, k_rs}, V{(const bf16*)v, v_bs, v_rs}, O{(const bf16*)o, o_bs, o_rs},
       GO{(const bf16*)go, go_bs, go_rs};
   ViewW DQ{(bf16*)dq, dq_bs, dq_rs}, DK{(bf16*)dk, dk_bs, dk_rs}, DV{(bf16*)dv, dv_bs, dv_rs};
   const float scale = 1.f / sqrtf((float)dh);
   switch (dh) {
-    case 16: return launch_bwd<16>(Q, K, V, O, GO, DQ, DK, DV, lse, B, H, Sq, Sk, scale, st);
-    case 32: return launch_bwd<32>(Q, K, V, O, GO, DQ, DK, DV, lse, B, H, Sq, Sk, scale, st);
-    default: return launch_bwd<64>(Q, K, V, O, GO, DQ, DK, DV, lse, B, H, Sq, Sk, scale, st);
+    case 16: return launch_bwd<16>(Q, K, V, O, GO, DQ, DK, DV, lse, B, H, Sq, Sk, scale, drop, seed_dev, st);
+    case 32: return launch_bwd<32>(Q, K, V, O, GO, DQ, DK, DV, lse, B, H, Sq, Sk, scale, drop, seed_dev, st);
+    default: return launch_bwd<64>(Q, K, V, O, GO, DQ, DK, DV, lse, B, H, Sq, Sk, scale, drop, seed_dev, st);
   }
 }

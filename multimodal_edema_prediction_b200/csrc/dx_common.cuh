@@ -78,6 +78,41 @@ __device__ __forceinline__ void dx_st8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// ---- dropout ---------------------------------------------------------------------------
+// Counter-based generator shared by every kernel that drops activations (attention probabilities, FFN hidden, heads):
+// element `idx` of a dropout site is kept iff splitmix64(seed + idx * golden) >> 32 >= p * 2^32, and scaled by 1/(1-p).
+// Nothing is stored: the backward pass regenerates the mask from (seed, idx).  tests/ops_emulator.py and the oracle restate
+// the same function in numpy, so parity tests run both sides on identical masks.  (torch's Philox stream is not
+// reproduced: the reference's dropout masks are not a portable contract.)
+__host__ __device__ __forceinline__ uint32_t dx_rng32(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+struct DxDrop {
+  unsigned long long seed;
+  uint32_t thresh;   // 0 = dropout disabled
+  float scale;
+};
+static inline DxDrop dx_make_drop(float p, unsigned long long seed) {
+  DxDrop d;
+  d.seed = seed;
+  double t = (double)p * 4294967296.0;
+  d.thresh = p > 0.f ? (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t) : 0u;
+  d.scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  return d;
+}
+// seed_dev: optional device-resident offset (advanced once per step so that a replayed CUDA graph draws fresh masks)
+__device__ __forceinline__ DxDrop dx_drop_resolve(DxDrop d, const unsigned long long* seed_dev) {
+  if (seed_dev) d.seed += seed_dev[0];
+  return d;
+}
+__device__ __forceinline__ float dx_drop_factor(const DxDrop& d, unsigned long long idx) {
+  return dx_rng32(d.seed, idx) >= d.thresh ? d.scale : 0.f;
+}
+
 // ---- reductions ----------------------------------------------------------------------
 __device__ __forceinline__ float dx_warp_sum(float v) {
 #pragma unroll

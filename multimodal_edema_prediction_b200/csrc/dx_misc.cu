@@ -196,6 +196,29 @@ inline int grid_for(long long n) {
 
 }  // namespace
 
+// y = x * keep / (1 - p), keep regenerated from (seed, flat index): forward and backward of nn.Dropout are the same call
+template <typename T>
+__global__ void __launch_bounds__(NT) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, DxDrop d,
+                                                    const unsigned long long* __restrict__ seed_dev) {
+  d = dx_drop_resolve(d, seed_dev);
+  for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT)
+    dx_st(y + i, dx_ld(x + i) * dx_drop_factor(d, (unsigned long long)i));
+}
+
+// out[n] = sum_c a[n,c] * (b[n,c] - bias[c])   (FFN ScaleNorm-backward row dot when dropout sits between GELU and W2)
+template <typename T>
+__global__ void __launch_bounds__(256) rowdot_bias_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int N, int C) {
+  const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const T* ar = a + (long long)warp * C;
+  const T* br = b + (long long)warp * C;
+  float dot = 0.f;
+  for (int c = lane; c < C; c += 32) dot = fmaf(dx_ld(ar + c), dx_ld(br + c) - (bias ? bias[c] : 0.f), dot);
+  dot = dx_warp_sum(dot);
+  if (lane == 0) out[warp] = dot;
+}
+
 extern "C" {
 
 int dx_mean_rows(const void* x, float* y, int B, int T1, int T, int64_t E, int dtype, void* stream) {
@@ -344,6 +367,25 @@ int dx_sumsq(const float* x, int64_t n, float* out, void* stream) {
 int dx_clip_factor(const float* sumsq, float max_norm, float* clip, void* stream) {
   DX_CHECK_ARG(sumsq && clip, "dx_clip_factor: bad arguments");
   clip_factor_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, clip);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
+int dx_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev, int dtype, void* stream) {
+  DX_CHECK_ARG(x && y && n > 0 && p >= 0.f && p < 1.f, "dx_dropout: bad arguments (0 <= p < 1)");
+  const DxDrop d = dx_make_drop(p, seed);
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
+  if (dtype == DX_BF16) dropout_kernel<bf16><<<grid_for(n), NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, n, d, sd);
+  else dropout_kernel<float><<<grid_for(n), NT, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, n, d, sd);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
+int dx_rowdot_bias(const void* a, const void* b, const float* bias, float* out, int N, int C, int dtype, void* stream) {
+  DX_CHECK_ARG(a && b && out && N > 0 && C > 0, "dx_rowdot_bias: bad arguments");
+  const int grid = dx_ceil_div((long long)N * 32, 256);
+  if (dtype == DX_BF16) rowdot_bias_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, bias, out, N, C);
+  else rowdot_bias_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, (const float*)b, bias, out, N, C);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }

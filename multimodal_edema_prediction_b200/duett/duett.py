@@ -6,8 +6,9 @@ libduett_b200.so (backbone.py / functional.py / ops.py).  There is no CPU path: 
 
 Not inherited from the reference (documented divergences):
   * `forward` does not overwrite the caller's xs_feats count columns in place (duett/duett.py:252);
-  * transformer_dropout / head dropout > 0 in training mode raise NotImplementedError for now (the reference's RNG stream
-    could not be matched anyway; parity configs use 0 — SURVEY §7);
+  * dropout (transformer_dropout on attention probabilities and FFN hidden, nn.Dropout in the MLP heads) draws its masks
+    from the kernels' own counter-based generator (ops.drop_seed / dx_dropout), not from torch's Philox stream: same
+    distribution and scaling, different bits — the reference's masks are not a portable contract;
   * Lightning is not in the image, so `Model` is an nn.Module that duck-types the LightningModule hooks it needs
     (`device`, `log`, `training_step`, `configure_optimizers`, `load_from_checkpoint`, `on_load_checkpoint`, `freeze`).
 """
@@ -22,7 +23,7 @@ import torch.nn.functional as F
 
 from .. import ops, state_keys
 from ..backbone import DuettEncodeFn, ENC_KEYS, TimeEmbedAssembleFn
-from ..functional import (BatchNorm2dFn, BCELogitsFn, GatherVecFn, MaskedMseBceFn, cast, linear)
+from ..functional import (BatchNorm2dFn, BCELogitsFn, GatherVecFn, MaskedMseBceFn, cast, dropout, linear)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -64,8 +65,7 @@ class DxSequential(nn.Sequential):
                     i += 1
                 x = linear(x if x.dtype == torch.float32 else cast(x, torch.float32), m.weight, m.bias, act)
             elif isinstance(m, nn.Dropout):
-                if m.p > 0 and self.training:
-                    raise NotImplementedError("dropout > 0 in training mode is not implemented in the B200 path yet")
+                x = dropout(x, m.p, self.training)
             elif isinstance(m, (BatchNormLastDim, nn.LayerNorm)) or hasattr(m, "dx_forward"):
                 x = m(x)
             else:
@@ -422,14 +422,11 @@ class Model(nn.Module):
         add("full_event_embedding.weight", self.full_event_embedding.weight)
         for kind, lst in (("event", self.event_transformers), ("time", self.time_transformers)):
             for l, enc in enumerate(lst):
-                if enc.dropout > 0 and self.training:
-                    raise NotImplementedError("transformer_dropout > 0 in training mode is not implemented in the B200 "
-                                              "path yet")
                 for k in ENC_KEYS:
                     add(f"{kind}_transformers.{l}.{k}", getattr(enc, k))
         spec = dict(names=names, d=self.d_embedding, V=self.d_time_series_num, T=None, n_layers=self.n_duett_layers,
                     heads=self.n_transformer_head, act_dtype=at, training=self.training, final_norm=self.final_norm,
-                    emb_rm=e.bn_rm, emb_rv=e.bn_rv)
+                    emb_rm=e.bn_rm, emb_rv=e.bn_rv, dropout=float(self.transformer_dropout))
         return spec, params
 
     def encode(self, x):

@@ -186,12 +186,14 @@ def cast(x, dtype):
 
 
 class AttentionFn(torch.autograd.Function):
-    """softmax(q k^T / sqrt(dh)) v, no mask. q [B,Sq,D], k/v [B,Sk,D]; last dim dense, other strides free."""
+    """dropout(softmax(q k^T / sqrt(dh))) v, no mask. q [B,Sq,D], k/v [B,Sk,D]; last dim dense, other strides free.
+    drop_p > 0: dropout on the attention probabilities (nn.MultiheadAttention(dropout=...) in training mode)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, heads):
-        o, lse = ops.attn_fwd(q, k, v, heads)
-        ctx.heads = heads
+    def forward(ctx, q, k, v, heads, drop_p=0.0):
+        drop = (drop_p, ops.drop_seed("attn", drop_p, (q.shape[0], heads, q.shape[1], k.shape[1]))) if drop_p > 0 else None
+        o, lse = ops.attn_fwd(q, k, v, heads, drop)
+        ctx.heads, ctx.drop = heads, drop
         ctx.save_for_backward(q, k, v, o, lse)
         return o
 
@@ -202,8 +204,30 @@ class AttentionFn(torch.autograd.Function):
         dq, dk, dv = torch.empty_like(q, memory_format=torch.contiguous_format), \
             torch.empty_like(k, memory_format=torch.contiguous_format), \
             torch.empty_like(v, memory_format=torch.contiguous_format)
-        ops.attn_bwd(q, k, v, o, go, lse, ctx.heads, dq, dk, dv)
-        return dq, dk, dv, None
+        ops.attn_bwd(q, k, v, o, go, lse, ctx.heads, dq, dk, dv, ctx.drop)
+        return dq, dk, dv, None, None
+
+
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout in training mode: y = x * keep / (1-p); the backward regenerates the mask from the saved seed."""
+
+    @staticmethod
+    def forward(ctx, x, p, tag):
+        x = x.contiguous()
+        ctx.p, ctx.seed = p, ops.drop_seed(tag, p, x.shape)
+        return ops.dropout(x, p, ctx.seed)
+
+    @staticmethod
+    def backward(ctx, gy):
+        return ops.dropout(gy.contiguous(), ctx.p, ctx.seed), None, None
+
+
+def dropout(x, p, training, tag="dropout"):
+    if not training or p <= 0:
+        return x
+    if p >= 1:
+        raise ops.L.DxError("dropout probability must be < 1")
+    return DropoutFn.apply(x, float(p), tag)
 
 
 # ---- losses (each returns scalars; gradients w.r.t. logits come from the same kernel launch) ----------------------------

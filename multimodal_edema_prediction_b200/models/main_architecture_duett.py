@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..duett.duett import DxSequential, Model as DuettBase
-from ..functional import AttentionFn, FusionLogitsFn, MeanRowsFn, cast, layer_norm, linear
+from ..functional import AttentionFn, FusionLogitsFn, MeanRowsFn, cast, dropout, layer_norm, linear
 
 
 class DuettFeatureExtractor(DuettBase):
@@ -57,8 +57,6 @@ class _MHA(nn.Module):
 
     def forward(self, q_in, kv_in, residual=None, same_kv=False):
         d = self.embed_dim
-        if self.dropout > 0 and self.training:
-            raise NotImplementedError("attention dropout > 0 in training mode is not implemented in the B200 path yet")
         W, b = self.in_proj_weight, self.in_proj_bias
         if same_kv and q_in is kv_in:
             qkv = linear(q_in, W, b)
@@ -67,7 +65,7 @@ class _MHA(nn.Module):
             q = linear(q_in, W[:d], b[:d])
             kv = linear(kv_in, W[d:], b[d:])
             k, v = kv[..., :d], kv[..., d:]
-        o = AttentionFn.apply(q, k, v, self.num_heads)
+        o = AttentionFn.apply(q, k, v, self.num_heads, float(self.dropout) if self.training else 0.0)
         return linear(o, self.out_proj.weight, self.out_proj.bias, res=residual)
 
 
@@ -88,13 +86,14 @@ class _PerceiverBlock(nn.Module):
     def forward(self, latents, kv, return_attn: bool = False):
         if return_attn:
             raise NotImplementedError("return_attn=True (attention-map visualisation) is not on the B200 hot path")
-        if self.dropout > 0 and self.training:
-            raise NotImplementedError("perceiver dropout > 0 in training mode is not implemented in the B200 path yet")
         q = layer_norm(latents, self.norm_q.weight, self.norm_q.bias)
         k = layer_norm(kv, self.norm_kv.weight, self.norm_kv.bias)
         latents = self.attn(q, k, residual=latents)
         f = layer_norm(latents, self.norm_ff.weight, self.norm_ff.bias)
         h = linear(f, self.ff[0].weight, self.ff[0].bias, ops.ACT_GELU)
+        h = dropout(h, self.ff[2].p, self.training, "perceiver.ff")
+        if self.ff[4].p > 0 and self.training:      # Dropout after the second Linear sits before the residual add
+            return latents + dropout(linear(h, self.ff[3].weight, self.ff[3].bias), self.ff[4].p, True, "perceiver.ff_out")
         return linear(h, self.ff[3].weight, self.ff[3].bias, res=latents)
 
 
@@ -155,10 +154,9 @@ class PatchDualPathologyPerceiver(nn.Module):
             hi = self.image_head(If).squeeze(-1)
             ht = self.temporal_head(Tf).squeeze(-1)
             ch = self.correction_head
-            if self.head_dropout > 0 and self.training:
-                raise NotImplementedError("head dropout > 0 in training mode is not implemented in the B200 path yet")
             c = layer_norm(Tf, ch[0].weight, ch[0].bias)
             c = linear(c, ch[1].weight, ch[1].bias, ops.ACT_GELU)
+            c = dropout(c, ch[3].p, self.training, "correction_head")
             ts_correction = linear(c, ch[4].weight, None).squeeze(-1)
             img_logits, ts_logits, scaled_correction, fusion_logits = FusionLogitsFn.apply(
                 hi, ht, ts_correction, self.image_label_bias, self.temporal_label_bias, self.beta)

@@ -155,8 +155,65 @@ def _view3(t):
     return t, t.stride(0), t.stride(1)
 
 
-def attn_fwd(q, k, v, heads):
-    """q [B,Sq,h*dh], k/v [B,Sk,h*dh] (strided views allowed) -> o [B,Sq,h*dh], lse [B,h,Sq]."""
+# ---- dropout seeds --------------------------------------------------------------------------------------------------
+# Every dropout site (attention probabilities, FFN hidden, nn.Dropout modules) draws a unique constant seed when it runs;
+# the kernels add the device-resident step counter to it, so a captured CUDA graph draws fresh masks on every replay once
+# the training loop calls advance_drop_step() (captured with the step).  The forward call's seed is kept by the autograd
+# node and handed to the backward call, which regenerates the same mask.  Determinism follows torch.manual_seed.
+_DROP = {"base": None, "site": 0, "dev": None}
+DROP_LOG = None      # tests set this to a list: every site appends (tag, p, seed, shape)
+
+
+def drop_seed(tag="", p=0.0, shape=None):
+    if _DROP["base"] is None:
+        _DROP["base"] = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & 0xFFFFFFFFFFFFFFFF
+    _DROP["site"] += 1
+    seed = (_DROP["base"] + _DROP["site"] * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    if DROP_LOG is not None:
+        DROP_LOG.append((tag, float(p), seed, tuple(shape) if shape is not None else None))
+    return seed
+
+
+def reset_drop_seeds(seed=None):
+    """Restart the site sequence (tests; torch.manual_seed alone does not rewind it)."""
+    _DROP["base"], _DROP["site"] = (None if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF), 0
+    if _DROP["dev"] is not None:
+        _DROP["dev"].zero_()
+
+
+def drop_step_counter(device):
+    """Device-resident uint64 (stored as int64) added to every site seed."""
+    if _DROP["dev"] is None or _DROP["dev"].device != torch.device(device):
+        _DROP["dev"] = torch.zeros(1, device=device, dtype=torch.int64)
+    return _DROP["dev"]
+
+
+def advance_drop_step():
+    """Call once per optimisation step, outside forward..backward (capturable)."""
+    if _DROP["dev"] is not None:
+        _DROP["dev"].add_(1)
+
+
+def dropout(x, p, seed, out=None):
+    """out = x * keep / (1-p); calling it on the upstream gradient with the same (p, seed) is the backward pass."""
+    _chk(x)
+    y = x if out is x else (torch.empty_like(x) if out is None else out)
+    _call("dx_dropout", _p(x), _p(y), x.numel(), float(p), int(seed), _p(drop_step_counter(x.device)), _dt(x))
+    return y
+
+
+def rowdot_bias(a, b, bias):
+    """out[n] = sum_c a[n,c] * (b[n,c] - bias[c])."""
+    _chk(a); _chk(b)
+    N, C = a.shape
+    out = torch.empty(N, device=a.device, dtype=torch.float32)
+    _call("dx_rowdot_bias", _p(a), _p(b), _p(bias), _p(out), N, C, _dt(a))
+    return out
+
+
+def attn_fwd(q, k, v, heads, drop=None):
+    """q [B,Sq,h*dh], k/v [B,Sk,h*dh] (strided views allowed) -> o [B,Sq,h*dh], lse [B,h,Sq].
+    drop = (p, seed): dropout on the attention probabilities."""
     B, Sq, D = q.shape
     Sk = k.shape[1]
     dh = D // heads
@@ -166,11 +223,13 @@ def attn_fwd(q, k, v, heads):
     for t in (q, k, v, o):
         t_, bs, rs = _view3(t)
         args += [_p(t_), bs, rs]
-    _call("dx_attn_fwd", *args, _p(lse), B, heads, Sq, Sk, dh, _dt(q))
+    dp, dseed = (float(drop[0]), int(drop[1])) if drop else (0.0, 0)
+    _call("dx_attn_fwd", *args, _p(lse), B, heads, Sq, Sk, dh, _dt(q), dp, dseed,
+          _p(drop_step_counter(q.device)) if drop else None)
     return o, lse
 
 
-def attn_bwd(q, k, v, o, go, lse, heads, dq, dk, dv):
+def attn_bwd(q, k, v, o, go, lse, heads, dq, dk, dv, drop=None):
     B, Sq, D = q.shape
     Sk = k.shape[1]
     dh = D // heads
@@ -179,7 +238,9 @@ def attn_bwd(q, k, v, o, go, lse, heads, dq, dk, dv):
     for t in (q, k, v, o, go, dq, dk, dv):
         t_, bs, rs = _view3(t)
         args += [_p(t_), bs, rs]
-    _call("dx_attn_bwd", *args, _p(lse), _p(Dws), B, heads, Sq, Sk, dh, _dt(q))
+    dp, dseed = (float(drop[0]), int(drop[1])) if drop else (0.0, 0)
+    _call("dx_attn_bwd", *args, _p(lse), _p(Dws), B, heads, Sq, Sk, dh, _dt(q), dp, dseed,
+          _p(drop_step_counter(q.device)) if drop else None)
 
 
 # ---- embedding ---------------------------------------------------------------------------------------------------------

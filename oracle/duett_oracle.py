@@ -166,8 +166,34 @@ def scale_norm(x, g, mode="normalize"):
     return xf / (n * dim ** -0.5).clamp_min(1e-5) * g.float()
 
 
-def encoder(P, prefix, x, cfg: DuettConfig):
-    """One x_transformers.Encoder(depth=1) exactly as constructed at duett/duett.py:95-105."""
+def keep_factor(seed, n, p, step=0):
+    """The kernels' dropout generator restated (csrc/dx_common.cuh dx_rng32): keep/(1-p) over flat indices 0..n-1, keep iff
+    splitmix64(seed + idx * 0x9E3779B97F4A7C15) >> 32 >= p * 2^32.  torch's Philox masks are not reproducible outside
+    torch, so dropout parity is checked with both sides on THIS generator (the seeds are read back from the product)."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64)
+        z = (np.uint64((int(seed) + int(step)) & 0xFFFFFFFFFFFFFFFF) + idx * np.uint64(0x9E3779B97F4A7C15)) & M
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M
+        z = z ^ (z >> np.uint64(31))
+        r = z >> np.uint64(32)
+    thresh = min(int(float(np.float32(p)) * 4294967296.0), 4294967295)
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return torch.from_numpy(np.where(r >= thresh, scale, np.float32(0)).astype(np.float32))
+
+
+def _drop(x, drop, key):
+    """x * mask/(1-p) when `drop` (dict site -> (p, seed)) names this site; identity otherwise."""
+    if not drop or key not in drop:
+        return x
+    p, seed = drop[key]
+    return x * keep_factor(seed, x.numel(), p).reshape(x.shape).to(x.dtype)
+
+
+def encoder(P, prefix, x, cfg: DuettConfig, drop=None):
+    """One x_transformers.Encoder(depth=1) exactly as constructed at duett/duett.py:95-105 (attn_dropout on the softmax
+    output, ff_dropout after the GELU: sites `<prefix>.attn`, `<prefix>.ff` of `drop`)."""
     B, N, dim = x.shape
     h, d = cfg.n_heads, cfg.d_embedding
     dh = d // h
@@ -178,10 +204,12 @@ def encoder(P, prefix, x, cfg: DuettConfig):
     q, k, v = (t.reshape(B, N, h, dh).permute(0, 2, 1, 3) for t in (q, k, v))
     sim = torch.matmul(q, k.transpose(-1, -2)) * dh ** -0.5
     attn = torch.softmax(sim, dim=-1, dtype=torch.float32).to(sim.dtype)
+    attn = _drop(attn, drop, prefix + ".attn")
     o = torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(B, N, h * dh)
     x = x + F.linear(o, P[f"{prefix}.layers.0.1.to_out.weight"])
     f = scale_norm(x, P[f"{prefix}.layers.1.0.0.g"], cfg.scalenorm_eps_mode)
     hdn = F.gelu(F.linear(f, P[f"{prefix}.layers.1.1.ff.0.0.weight"], P[f"{prefix}.layers.1.1.ff.0.0.bias"]))
+    hdn = _drop(hdn, drop, prefix + ".ff")
     x = x + F.linear(hdn, P[f"{prefix}.layers.1.1.ff.2.weight"], P[f"{prefix}.layers.1.1.ff.2.bias"])
     if cfg.final_norm:
         x = scale_norm(x, P[f"{prefix}.final_norm.g"], cfg.scalenorm_eps_mode)
@@ -234,7 +262,7 @@ def time_embeddings(P, cfg: DuettConfig, xs_times, training, stats_out=None):
     return torch.cat((t, rep), dim=1)
 
 
-def encode(P, cfg: DuettConfig, xs_static, xs_feats, xs_times, training=True, stats_out=None, return_psi=False):
+def encode(P, cfg: DuettConfig, xs_static, xs_feats, xs_times, training=True, stats_out=None, return_psi=False, drop=None):
     """DuettFeatureExtractor.encode -> transformed [B,T+1,E'] (models/main_architecture_duett.py:31-94)."""
     psi, event_masked = embed_psi(P, cfg, xs_static, xs_feats, training, stats_out)
     te = time_embeddings(P, cfg, xs_times, training, stats_out)
@@ -242,9 +270,9 @@ def encode(P, cfg: DuettConfig, xs_static, xs_feats, xs_times, training=True, st
     pos_e = P["full_event_embedding.weight"]
     for l in range(cfg.n_layers):
         ev = psi.permute(0, 2, 1, 3).reshape(B, V1, T1 * d) + pos_e           # event view: token = variable
-        ev = encoder(P, f"event_transformers.{l}", ev, cfg)
+        ev = encoder(P, f"event_transformers.{l}", ev, cfg, drop)
         tv = ev.reshape(B, V1, T1, d).permute(0, 2, 1, 3).reshape(B, T1, V1 * d) + te   # time view: token = time bin
-        psi = encoder(P, f"time_transformers.{l}", tv, cfg).reshape(B, T1, V1, d)
+        psi = encoder(P, f"time_transformers.{l}", tv, cfg, drop).reshape(B, T1, V1, d)
     out = psi.reshape(B, T1, V1 * d)
     if return_psi:
         return out, psi, event_masked
@@ -412,11 +440,12 @@ def init_student_head(cfg: DuettConfig, seed=1, head_hidden=128):
     return P
 
 
-def student_forward(P, H, cfg, xs_static, xs_feats, xs_times, pool="mean", training=True, stats_out=None):
-    """StudentModel.forward (models/main_architecture_duett.py:1221-1235); head dropout off (p=0 / eval)."""
-    tok = encode(P, cfg, xs_static, xs_feats, xs_times, training, stats_out)
+def student_forward(P, H, cfg, xs_static, xs_feats, xs_times, pool="mean", training=True, stats_out=None, drop=None):
+    """StudentModel.forward (models/main_architecture_duett.py:1221-1235); `drop`: dropout sites (encoders, "head")."""
+    tok = encode(P, cfg, xs_static, xs_feats, xs_times, training, stats_out, drop=drop)
     feat = tok[:, -1] if pool == "rep_token" else tok[:, :-1].mean(1)
     h = F.gelu(F.linear(feat, H["head.0.weight"], H["head.0.bias"]))
+    h = _drop(h, drop, "head")
     return F.linear(h, H["head.3.weight"], H["head.3.bias"]).squeeze(-1)
 
 

@@ -147,7 +147,36 @@ def rowdot_scale(a, g, row_scale):
     return rd
 
 
-def _attn(q, k, v, heads):
+def keep_factor(seed, n, p, step=0):
+    """Restatement of dx_rng32 / dx_drop_factor (csrc/dx_common.cuh): float32 tensor [n] of keep/(1-p) over flat indices."""
+    import numpy as np
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64)
+        z = (np.uint64((int(seed) + int(step)) & 0xFFFFFFFFFFFFFFFF) + idx * np.uint64(0x9E3779B97F4A7C15)) & M
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M
+        z = z ^ (z >> np.uint64(31))
+        r = (z >> np.uint64(32)).astype(np.uint64)
+    thresh = min(int(float(np.float32(p)) * 4294967296.0), 4294967295)
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return torch.from_numpy(np.where(r >= thresh, scale, np.float32(0)).astype(np.float32))
+
+
+def dropout(x, p, seed, out=None):
+    y = (x.float() * keep_factor(seed, x.numel(), p).reshape(x.shape)).to(x.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def rowdot_bias(a, b, bias):
+    bb = b.float() - (bias.float() if bias is not None else 0.0)
+    return (a.float() * bb).sum(1)
+
+
+def _attn(q, k, v, heads, drop=None):
     B, Sq, D = q.shape
     dh = D // heads
     qh = q.float().reshape(B, Sq, heads, dh).transpose(1, 2)
@@ -155,19 +184,22 @@ def _attn(q, k, v, heads):
     vh = v.float().reshape(B, -1, heads, dh).transpose(1, 2)
     s = qh @ kh.transpose(-1, -2) / math.sqrt(dh)
     lse = torch.logsumexp(s, -1)
-    o = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Sq, D)
+    pr = torch.softmax(s, -1)
+    if drop:
+        pr = pr * keep_factor(drop[1], pr.numel(), drop[0]).reshape(pr.shape)      # index ((b*H+h)*Sq+q)*Sk+k
+    o = (pr @ vh).transpose(1, 2).reshape(B, Sq, D)
     return o, lse
 
 
-def attn_fwd(q, k, v, heads):
-    o, lse = _attn(q, k, v, heads)
+def attn_fwd(q, k, v, heads, drop=None):
+    o, lse = _attn(q, k, v, heads, drop)
     return o.to(q.dtype).contiguous(), lse.contiguous()
 
 
-def attn_bwd(q, k, v, o, go, lse, heads, dq, dk, dv):
+def attn_bwd(q, k, v, o, go, lse, heads, dq, dk, dv, drop=None):
     with torch.enable_grad():
         qq, kk, vv = (t.detach().float().clone().requires_grad_(True) for t in (q, k, v))
-        oo, _ = _attn(qq, kk, vv, heads)
+        oo, _ = _attn(qq, kk, vv, heads, drop)
         gq, gk, gv = torch.autograd.grad(oo, (qq, kk, vv), go.float())
     dq.copy_(gq); dk.copy_(gk); dv.copy_(gv)
 
@@ -450,7 +482,7 @@ def binary_auc(logits, labels, apply_sigmoid=True):
     return torch.tensor([auroc, auprc, n_pos, float(len(y))], dtype=torch.float64)
 
 
-EMULATED = ["binary_auc", "sum_n", "gemm_", "relayout_fwd", "relayout_bwd", "colsum", "axpy", "axpy_f32", "cast", "scalenorm_scale", "rowdot_scale",
+EMULATED = ["binary_auc", "sum_n", "dropout", "rowdot_bias", "gemm_", "relayout_fwd", "relayout_bwd", "colsum", "axpy", "axpy_f32", "cast", "scalenorm_scale", "rowdot_scale",
             "attn_fwd", "attn_bwd", "embed_fwd", "embed_bwd", "bn2d_fwd", "bn2d_bwd", "layernorm_fwd", "layernorm_bwd",
             "mean_rows", "mean_rows_bwd", "gather_vec", "scatter_vec", "kd_loss", "bce_logits", "masked_mse_bce",
             "masked_bce_cols", "aux_residual_kl", "require_device", "act_bwd", "act_fwd", "scale_dev", "sum_div_acc", "fusion_logits",

@@ -191,3 +191,59 @@ def test_evaluate_binary_surface(emu):
     assert set(res) == {"auroc", "auprc", "n", "pos_frac"}
     for name in ("make_teacher_forward", "make_teacher_aux_forward", "make_student_forward"):
         assert callable(getattr(evaluator, name)())
+
+
+def test_student_step_with_dropout_host_logic(emu):
+    """Dropout orchestration of the product (sites and seeds, in-place drop of the saved FFN hidden, mask applied to the
+    GELU' outputs, row-dot recomputed after it, attention-probability mask in forward and backward) against the oracle
+    replaying the same step with masks from the same generator (seeds read back from the product's dropout log)."""
+    from oracle import duett_oracle as O
+    from multimodal_edema_prediction_b200 import ops
+    from multimodal_edema_prediction_b200.loss.losses_duett import StudentKDLoss
+    from multimodal_edema_prediction_b200.models.main_architecture_duett import DuettFeatureExtractor, StudentModel
+    cfg = O.DuettConfig(d_static_num=3, d_time_series_num=5, n_timesteps=4, d_embedding=8, n_layers=2, d_feedforward=96)
+    B = 6
+    P, H = O.init_params(cfg, seed=21), O.init_student_head(cfg, seed=22, head_hidden=16)
+    batch = O.synth_batch(cfg, B, seed=777)
+    duett = DuettFeatureExtractor(cfg.d_static_num, cfg.V, 1, d_embedding=cfg.d_embedding, n_duett_layers=cfg.n_layers,
+                                  masked_transform_timesteps=cfg.T, max_len=cfg.T, d_feedforward=cfg.d_feedforward,
+                                  pretrain=False, precision="fp32", transformer_dropout=0.25)
+    student = StudentModel(duett, pool="mean", head_hidden=16, head_dropout=0.1)
+    sd = {"duett." + k: v for k, v in P.items()}
+    sd.update(H)
+    student.load_state_dict(sd, strict=True)
+    student.train()
+    x = (batch["x_ts"], batch["x_static"], list(batch["bin_ends"]))
+    z_t = torch.randn(B, generator=torch.Generator().manual_seed(5)) * 1.5
+    ops.reset_drop_seeds(1234)
+    ops.DROP_LOG = []
+    try:
+        z = student(*x)
+        log = list(ops.DROP_LOG)
+    finally:
+        ops.DROP_LOG = None
+    drop = {("head" if tag == "dropout" else tag): (p, seed) for tag, p, seed, _ in log}
+    assert sorted(drop) == sorted([f"{k}_transformers.{l}.{s}" for k in ("event", "time") for l in range(2) for s in ("attn", "ff")]
+                                  + ["head"])
+    StudentKDLoss(kd_T=4.0, kd_alpha=0.5)(z, z_t, batch["y"])["total"].backward()
+    xs_static, xs_ts, xs_times, _ = O.feats_to_input(batch["x_ts"], batch["x_static"], batch["bin_ends"], cfg.T)
+    Pl = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P.items()}
+    Hl = {k: v.clone().requires_grad_(True) for k, v in H.items()}
+    z_ref = O.student_forward(Pl, Hl, cfg, xs_static, xs_ts, xs_times, pool="mean", drop=drop)
+    O.student_kd_loss(z_ref, z_t, batch["y"], 4.0, 0.5, None)["total"].backward()
+    assert rel(z, z_ref) < TOL
+    want = {"duett." + k: v.grad for k, v in Pl.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    want.update({k: v.grad for k, v in Hl.items()})
+    _grad_check(_ref_keyed_grads(student), want)
+    # a second training forward draws new seeds (fresh masks); eval mode draws none
+    ops.DROP_LOG = []
+    try:
+        student(*x)
+        assert len(ops.DROP_LOG) == 9 and {s for _, _, s, _ in ops.DROP_LOG}.isdisjoint({s for _, _, s, _ in log})
+        student.eval()
+        ops.DROP_LOG = []
+        with torch.no_grad():
+            student(*x)
+        assert ops.DROP_LOG == []
+    finally:
+        ops.DROP_LOG = None

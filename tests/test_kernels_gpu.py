@@ -398,3 +398,38 @@ def test_bin_events_bit_exact_vs_reference_golden(ops):
     bad.loc[0, "slot_idx"] = -T - 1
     with pytest.raises(IndexError):
         md.build_stay_tensor(bad, means, stds, T, all_vars, all_counts)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_dropout_matches_generator_spec(ops, dt):
+    """dx_dropout against the numpy restatement of the generator (tests/ops_emulator.keep_factor): identical mask bits,
+    keep rate ~ 1-p, backward = same call on the gradient."""
+    x = rnd(37, 129, dtype=dt, seed=80)
+    for p, seed in ((0.1, 12345), (0.5, 2 ** 63 + 7)):
+        y = ops.dropout(x, p, seed)
+        want = E.dropout(x.cpu(), p, seed)
+        assert rel(y, want) < (1e-6 if dt == torch.float32 else 4e-3)
+        assert torch.equal((y == 0).cpu(), (want == 0))
+        keep = float((y != 0).float().mean())
+        assert abs(keep - (1 - p)) < 0.03
+    a, b, bias = rnd(50, 96, dtype=dt, seed=81), rnd(50, 96, dtype=dt, seed=82), rnd(96, seed=83)
+    assert rel(ops.rowdot_bias(a, b, bias), E.rowdot_bias(*cpu(a, b, bias))) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("S,D,H", [(129, 128, 2), (33, 64, 2), (35, 24, 2)])
+def test_attention_dropout_fwd_bwd(ops, dt, S, D, H):
+    """Attention-probability dropout in the tensor-core (bf16, dh 32/64) and SIMT kernels against the emulator running on
+    the same generator; the backward regenerates the mask."""
+    B, drop = 3, (0.3, 987654321)
+    qkv = rnd(B, S, 3 * D, dtype=dt, seed=84, scale=0.7)
+    q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    o, lse = ops.attn_fwd(q, k, v, H, drop)
+    ro, rlse = E.attn_fwd(*cpu(q, k, v), H, drop)
+    assert rel(o, ro) < TOL[dt] * 2 and rel(lse, rlse) < 1e-3
+    go = rnd(B, S, D, dtype=dt, seed=85)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(q, k, v, o, go, lse, H, dqkv[:, :, :D], dqkv[:, :, D:2 * D], dqkv[:, :, 2 * D:], drop)
+    rq, rk, rv = torch.empty(B, S, D), torch.empty(B, S, D), torch.empty(B, S, D)
+    E.attn_bwd(*cpu(q, k, v, o, go, lse), H, rq, rk, rv, drop)
+    assert rel(dqkv, torch.cat([rq, rk, rv], 2)) < TOL[dt] * 2

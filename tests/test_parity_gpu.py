@@ -305,3 +305,59 @@ def test_auroc_on_fixed_synthetic_eval_set(mode, dauc):
         assert rel(zs, zr) < 1e-3
     else:
         assert float(((zs - zs.mean()) - (zr - zr.mean())).norm() / (zr - zr.mean()).norm()) < 0.1
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_student_step_with_dropout_vs_oracle(mode, tol):
+    """transformer_dropout (attention probabilities + FFN hidden of every axis encoder) and head dropout in training mode:
+    the product's dropout sites log their (probability, seed); the oracle replays the step with masks drawn from the same
+    counter-based generator, so logits, loss and every gradient are compared on identical masks."""
+    from multimodal_edema_prediction_b200 import ops
+    from multimodal_edema_prediction_b200.loss.losses_duett import StudentKDLoss
+    from multimodal_edema_prediction_b200.models.main_architecture_duett import DuettFeatureExtractor, StudentModel
+    cfg = O.DuettConfig(d_static_num=24, d_time_series_num=34, n_timesteps=24, d_embedding=32, n_layers=2)
+    B = 8
+    P, H = O.init_params(cfg, seed=21), O.init_student_head(cfg, seed=22)
+    batch = O.synth_batch(cfg, B, seed=777)
+    duett = DuettFeatureExtractor(cfg.d_static_num, cfg.V, 1, d_embedding=cfg.d_embedding, n_duett_layers=cfg.n_layers,
+                                  masked_transform_timesteps=cfg.T, max_len=cfg.T, d_feedforward=cfg.d_feedforward,
+                                  pretrain=False, precision=mode, transformer_dropout=0.25)
+    student = StudentModel(duett, pool="mean", head_hidden=128, head_dropout=0.1)
+    sd = {"duett." + k: v for k, v in P.items()}
+    sd.update(H)
+    student.load_state_dict(sd, strict=True)
+    student.cuda().train()
+    x = (batch["x_ts"], batch["x_static"], list(batch["bin_ends"]))
+    z_t = torch.randn(B, generator=torch.Generator().manual_seed(5)) * 1.5
+    ops.reset_drop_seeds(1234)
+    ops.DROP_LOG = []
+    try:
+        z = student(*x)
+        log = list(ops.DROP_LOG)
+    finally:
+        ops.DROP_LOG = None
+    drop = {("head" if tag == "dropout" else tag): (p, seed) for tag, p, seed, _ in log}
+    assert len(drop) == 4 * cfg.n_layers + 1 and all(p > 0 for p, _ in drop.values()), sorted(drop)
+    losses = StudentKDLoss(kd_T=4.0, kd_alpha=0.5)(z, z_t.cuda(), batch["y"].cuda())
+    losses["total"].backward()
+    xs_static, xs_ts, xs_times, _ = O.feats_to_input(batch["x_ts"], batch["x_static"], batch["bin_ends"], cfg.T)
+    Pl = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P.items()}
+    Hl = {k: v.clone().requires_grad_(True) for k, v in H.items()}
+    z_ref = O.student_forward(Pl, Hl, cfg, xs_static, xs_ts, xs_times, pool="mean", drop=drop)
+    L_ref = O.student_kd_loss(z_ref, z_t, batch["y"], 4.0, 0.5, None)
+    L_ref["total"].backward()
+    assert rel(z.cpu(), z_ref) < tol * (3 if mode == "fp32" else 6)
+    assert rel(losses["total"].cpu(), L_ref["total"]) < tol
+    want = {"duett." + k: v.grad for k, v in Pl.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    want.update({k: v.grad for k, v in Hl.items()})
+    got = _ref_keyed_grads(student)
+    _grad_check({k: got[k] for k in want}, want, tol * (1 if mode == "fp32" else 2.5), floor=5e-2)
+    # eval mode: dropout is the identity and no site draws a seed
+    student.eval()
+    ops.DROP_LOG = []
+    try:
+        with torch.no_grad():
+            student(*x)
+        assert ops.DROP_LOG == []
+    finally:
+        ops.DROP_LOG = None
