@@ -216,6 +216,18 @@ __device__ __forceinline__ void stage_store(uint32_t buf, void* base, long long 
   const uint32_t sp = buf + rsub * 128;
   const uint32_t pe = (uint32_t)((piece ^ rsub) << 4), po = (uint32_t)((piece ^ (rsub + 4)) << 4);
   const int rows = M - m_base - rsub;   // rows r = 4*i + rsub valid while 4*i < rows
+  if (rows > 28) {   // whole block inside the matrix (the common case): no per-row predicates
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint4 u;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                   : "r"(sp + i * 512 + ((i & 1) ? po : pe)));
+      *reinterpret_cast<uint4*>(gp) = u;
+      gp += gstep;
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (4 * i < rows) {
@@ -258,12 +270,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void lds8(uint32_t addr, float (&v)[8]) {
   uint4 u;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+  // bf16 -> f32 is a 16-bit left shift: low element = word << 16, high element = word & 0xffff0000 (one op each)
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 f = __bfloat1622float2(h[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
 __device__ __forceinline__ void sts8(uint32_t addr, const float (&v)[8]) {
@@ -327,10 +339,13 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
   const int m_off = CTAS == 2 ? (int)cluster_ctarank() * BM : 0;
   const int ustep = (int)gridDim.x / CTAS;
   const uint32_t empty_remote = CTAS == 2 ? mapa_u32(smem_u32(tmem_empty_bar), 0) : 0;   // the leader's tmem_empty_bar[0]
+  // the staged epilogue never runs with split-K (work unit == tile); each tile's coordinates are decoded once, one tile
+  // ahead (integer divisions), and serve both the cross-tile prefetch and the next iteration
+  int mi = 0, ni = 0, z = 0;
+  if ((int)blockIdx.x / CTAS < p.total_tiles) tile_decode(p, (int)blockIdx.x / CTAS, mi, ni, z);
   for (int unit = (int)blockIdx.x / CTAS; unit < p.total_tiles; unit += ustep, ++tcount) {
-    const int tile = unit / p.splits;
-    int mi, ni, z;
-    tile_decode(p, tile, mi, ni, z);
+    int mi2 = 0, ni2 = 0, z2 = -1;
+    if (unit + ustep < p.total_tiles) tile_decode(p, unit + ustep, mi2, ni2, z2);
     const int n0 = ni * BN;
     const int m0 = mi * (BM * CTAS) + m_off;
     const uint32_t slot = tcount & 1, use = tcount >> 1;
@@ -359,14 +374,10 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
         if (sc + 2 < nsc) {
           next = true;
         } else {
-          const int unit2 = unit + ustep;
-          if (unit2 < p.total_tiles) {
-            const int tile2 = unit2 / p.splits;
-            int mi2, ni2, z2;
-            tile_decode(p, tile2, mi2, ni2, z2);
+          if (z2 == z) {   // next tile exists and lies in the same batch slice: the pointers of `e` are valid for it
             nc2 = ni2 * BN + chalf * 64;
             m_base2 = mi2 * (BM * CTAS) + m_off + q * 32;
-            next = (z2 == z) && nc2 < e.N;   // same batch slice: the pointers of `e` are valid for it
+            next = nc2 < e.N;
           }
         }
         if (next) {
@@ -391,12 +402,14 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
         sphase ^= 1u << bi;
       }
       __syncwarp();
+      // piece p of this lane's row lives at row + ((p ^ (lane & 7)) << 4); the blocks are 1024 B aligned, so with the lane's
+      // swizzle term folded into the row address the piece address is one XOR with a compile-time constant
       const uint32_t bufR = stg + bi * STG_BYTES;
-      const uint32_t rowR = bufR + lane * 128;
-      const uint32_t rowX = stg + (ring + bi) * STG_BYTES + lane * 128;
+      const uint32_t rowR = bufR + lane * 128 + (lsw << 4);
+      const uint32_t rowX = stg + (ring + bi) * STG_BYTES + lane * 128 + (lsw << 4);
       // out2 is staged in place over the aux block when there is one (each lane rewrites the 16 B piece it has just read)
       const uint32_t bufO = has_x ? stg + (ring + bi) * STG_BYTES : bufO_own;
-      const uint32_t rowO = bufO + lane * 128;
+      const uint32_t rowO = bufO + lane * 128 + (lsw << 4);
       const uint32_t biasS = sbias + bb * 256;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -405,20 +418,23 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int piece = half * 4 + j;
-          const uint32_t po = ((uint32_t)piece ^ lsw) << 4;
+          const uint32_t px = (uint32_t)piece << 4;
           const int ncol = nc + piece * 8;
           float t[8], r[8], a[8], o2[8], bv[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
-          if (has_res) lds8(rowR + po, r);
-          if (has_x) lds8(rowX + po, a);
+          if (has_res) lds8(rowR ^ px, r);
+          if (has_x) lds8(rowX ^ px, a);
           if (has_b) lds_f8(biasS + piece * 32, bv);
-          if (row_ok && ncol < e.N) {   // N % 8 == 0 on this path: pieces are whole
-            if constexpr (CT) dx_epilogue_math_c<MASK>(rc, t, r, a, bv, o2, rs, rd);
-            else dx_epilogue_math<8>(e, rc, ncol, 8, t, r, a, a, o2, rs, rd);   // aux and cx are mutually exclusive: `a` is both
+          if constexpr (CT) {
+            // no bounds branch: out-of-range rows / columns hold zeros everywhere (operands, side blocks and bias are
+            // zero-filled by TMA / cp.async), contribute nothing to the row sums, and are never stored or flushed
+            dx_epilogue_math_c<MASK>(rc, t, r, a, bv, o2, rs, rd);
+          } else if (row_ok && ncol < e.N) {   // N % 8 == 0 on this path: pieces are whole
+            dx_epilogue_math<8>(e, rc, ncol, 8, t, r, a, a, o2, rs, rd);   // aux and cx are mutually exclusive: `a` is both
           }
-          sts8(rowR + po, t);
-          if (has_o2) sts8(rowO + po, o2);
+          sts8(rowR ^ px, t);
+          if (has_o2) sts8(rowO ^ px, o2);
         }
       }
       __syncwarp();
@@ -443,6 +459,7 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
       else mbar_arrive(tmem_empty_bar + slot);
     }
     if (row_ok) dx_epilogue_flush_row(e, m, rs, rd);
+    mi = mi2; ni = ni2; z = z2;
   }
 }
 
