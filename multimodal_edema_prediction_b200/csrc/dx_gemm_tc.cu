@@ -146,6 +146,19 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                "h"((uint16_t)3)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -411,10 +424,16 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
       const uint32_t bufO = has_x ? stg + (ring + bi) * STG_BYTES : bufO_own;
       const uint32_t rowO = bufO + lane * 128 + (lsw << 4);
       const uint32_t biasS = sbias + bb * 256;
+      // both 32-column halves of the item are requested before the first is used (one TMEM round trip per item)
+      uint32_t vr[2][32];
+      tmem_ld32_issue(acc + (uint32_t)(sc * 64), vr[0]);        // warp-collective
+      tmem_ld32_issue(acc + (uint32_t)(sc * 64 + 32), vr[1]);
+      tmem_ld_wait();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float v[32];
-        tmem_ld32(acc + (uint32_t)(sc * 64 + half * 32), v);  // warp-collective
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(vr[half][k]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int piece = half * 4 + j;
