@@ -271,6 +271,8 @@ def main():
     loss_evt = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {"pending": None, "losses": []}
 
+    copy_stream = torch.cuda.Stream(device=device)
+
     def e2e_collect():
         j = e2e_state["pending"]
         if j is not None:
@@ -287,8 +289,16 @@ def main():
             loss.backward()
             opt.step(grad_scale=red.finish())
         else:
-            xs_static, xs_ts, xs_times, _ = model.feats_to_input((hb["x_ts"], hb["x_static"], list(hb["bin_ends"])), B)
-            loss = gstep(xs_static=xs_static, xs_ts=xs_ts, xs_times=xs_times, y=hb["y"])
+            # this step's inputs go up on a copy stream (pinned staging -> H2D), so the transfer overlaps the previous
+            # step still running on the compute stream; the compute stream waits for it before the captured step
+            main = torch.cuda.current_stream()
+            with torch.cuda.stream(copy_stream):
+                xs_static, xs_ts, xs_times, _ = model.feats_to_input((hb["x_ts"], hb["x_static"], list(hb["bin_ends"])), B)
+                y_dev = hb["y"].to(device, non_blocking=True)
+            main.wait_stream(copy_stream)
+            for t_ in (xs_static, xs_ts, xs_times, y_dev):
+                t_.record_stream(main)
+            loss = gstep(xs_static=xs_static, xs_ts=xs_ts, xs_times=xs_times, y=y_dev)
         j = i & 1
         loss_pin[j].copy_(loss.detach().reshape(1).double(), non_blocking=True)      # device -> host read of the step's result
         loss_evt[j].record()

@@ -36,29 +36,48 @@ __global__ void __launch_bounds__(NT) dx_gemm_simt_kernel(const TI* __restrict__
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   const bool a_kmajor = (sak == 1), b_kmajor = (sbk == 1);
-  for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
-    // A tile: BM*BK = 1024 elements, 4 per thread
+  // register-staged software pipeline: the global loads of k-block i+1 are in flight while k-block i is multiplied
+  constexpr int AE = (BM * BK) / NT, BE = (BN * BK) / NT;
+  float ra[AE], rb[BE];
+  auto gload = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < (BM * BK) / NT; ++i) {
+    for (int i = 0; i < AE; ++i) {
       const int idx = t + i * NT;
       int m, k;
       if (a_kmajor) { k = idx % BK; m = idx / BK; } else { m = idx % BM; k = idx / BM; }
       const int gm = m0 + m, gk = k0 + k;
-      float v = 0.f;
-      if (gm < e.M && gk < k_hi) v = dx_ld(A + (long long)gm * sam + (long long)gk * sak);
-      As[k][m] = v;
+      ra[i] = (gm < e.M && gk < k_hi) ? dx_ld(A + (long long)gm * sam + (long long)gk * sak) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < (BN * BK) / NT; ++i) {
+    for (int i = 0; i < BE; ++i) {
       const int idx = t + i * NT;
       int n, k;
       if (b_kmajor) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
       const int gn = n0 + n, gk = k0 + k;
-      float v = 0.f;
-      if (gn < e.N && gk < k_hi) v = dx_ld(B + (long long)gn * sbn + (long long)gk * sbk);
-      Bs[k][n] = v;
+      rb[i] = (gn < e.N && gk < k_hi) ? dx_ld(B + (long long)gn * sbn + (long long)gk * sbk) : 0.f;
     }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int i = 0; i < AE; ++i) {
+      const int idx = t + i * NT;
+      int m, k;
+      if (a_kmajor) { k = idx % BK; m = idx / BK; } else { m = idx % BM; k = idx / BM; }
+      As[k][m] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < BE; ++i) {
+      const int idx = t + i * NT;
+      int n, k;
+      if (b_kmajor) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
+      Bs[k][n] = rb[i];
+    }
+  };
+  if (k_lo < k_hi) gload(k_lo);
+  for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
+    sstore();
     __syncthreads();
+    if (k0 + BK < k_hi) gload(k0 + BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
