@@ -144,10 +144,10 @@ class DuettEncodeFn(torch.autograd.Function):
         T1, V1 = T + 1, V + 1
         E, Ep = T1 * cfgd, V1 * cfgd
         det = {k: v.detach() for k, v in P.items()}
-        psi0, emean, erstd = ops.embed_fwd(xs_feats, V, cfgd, det["emb.w0"], det["emb.b0"], det["emb.bn_w"], det["emb.bn_b"],
-                                           spec["emb_rm"], spec["emb_rv"], det["emb.w4"], det["emb.b4"],
-                                           det["n_obs_embedding.weight"].view(-1), det["special_embeddings.weight"],
-                                           tab.detach().contiguous(), at, training)
+        psi0, emean, erstd, ehn = ops.embed_fwd(xs_feats, V, cfgd, det["emb.w0"], det["emb.b0"], det["emb.bn_w"],
+                                                det["emb.bn_b"], spec["emb_rm"], spec["emb_rv"], det["emb.w4"], det["emb.b4"],
+                                                det["n_obs_embedding.weight"].view(-1), det["special_embeddings.weight"],
+                                                tab.detach().contiguous(), at, training, return_hidden=True)
         encs = []
         src, src_rowsq, g_prev = psi0, None, None
         for l in range(L):
@@ -166,7 +166,7 @@ class DuettEncodeFn(torch.autograd.Function):
         out, _ = ops.relayout_fwd(src.view(B * T1, 1, 1, Ep), B * T1, 1, 1, Ep, src_rowsq=src_rowsq, g=g_prev,
                                   want_rowsq=False)
         ctx.spec, ctx.encs, ctx.P, ctx.B, ctx.det = spec, encs, P, B, det
-        ctx.emb_saved = (xs_feats, emean, erstd)
+        ctx.emb_saved = (xs_feats, emean, erstd, ehn)
         ctx.te_requires_grad = te.requires_grad
         ctx.tab_requires_grad = tab.requires_grad
         return out.view(B, T1, Ep)
@@ -233,13 +233,13 @@ class DuettEncodeFn(torch.autograd.Function):
             dte = dte.view(B, T1, Ep)
         dx_ts = None
         # embedding backward
-        xs_feats, emean, erstd = ctx.emb_saved
+        xs_feats, emean, erstd, ehn = ctx.emb_saved
         z = lambda n: sinks[n] if n in sinks else torch.zeros_like(P[n], dtype=torch.float32)
         eg = {"dW0": z("emb.w0"), "db0": z("emb.b0"), "dgamma": z("emb.bn_w"), "dbeta": z("emb.bn_b"), "dW4": z("emb.w4"),
               "db4": z("emb.b4"), "dnobs": z("n_obs_embedding.weight").view(-1), "dspecial": z("special_embeddings.weight")}
         dtab = ops.embed_bwd(xs_feats, V, cfgd, det["emb.w0"], det["emb.b0"], det["emb.bn_w"], det["emb.bn_b"],
-                             det["emb.w4"], det["n_obs_embedding.weight"].view(-1), emean, erstd, dpsi0, eg, training)
-        ctx.encs = ctx.det = None
+                             det["emb.w4"], det["n_obs_embedding.weight"].view(-1), emean, erstd, dpsi0, eg, training, hn=ehn)
+        ctx.encs = ctx.det = ctx.emb_saved = None
         grads = tuple(rets.get(n) for n in names)
         return (None, None, dtab if ctx.tab_requires_grad else None, dte) + grads
 

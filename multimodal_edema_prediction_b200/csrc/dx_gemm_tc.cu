@@ -5,16 +5,20 @@
 //   from the tensors as they sit in HBM, without transposed copies).  Grouped mode: blockIdx.z selects one of
 //   `batch` independent problems through the third dimension of the tensor maps.
 //
-// CTA = 128 x BN output tile, BLOCK_K = 64 (one 128 B swizzle row of bf16), STAGES-deep mbarrier ring.
+// Persistent kernel: every CTA (or CTA pair) loops over output tiles.  CTA tile = 128 x BN (BN in 64/128/192/256),
+// BLOCK_K = 64 (one 128 B swizzle row of bf16), STAGES-deep mbarrier operand ring, two TMEM accumulators (2*BN columns) so
+// the epilogue of tile i overlaps the mainloop of tile i+1.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..9 = epilogue (TMEM lane quadrant = warp % 4; the two
 // warps of a quadrant take alternate 64-column blocks, so every SM scheduler has two epilogue warps to interleave).
-// Large-K shapes use BN=256 (1 CTA per SM, 96 B/clk smem operand traffic per MMA); small-K, HBM-bound shapes use
-// BN=128 with 2 stages so that 2 CTAs share an SM and epilogues overlap mainloops.
+// CTAS = 2 (deep-K shapes): a cluster of two CTAs shares a 256 x BN tile through tcgen05.mma.cta_group::2 (see the kernel).
+// Work units run N-fastest or M-fastest (TcParams::raster_m), whichever keeps the larger operand block hot in L2; dW
+// GEMMs with too few tiles split K (red.global.add partial sums).
 //
 // Epilogue front-ends:
 //   STAGED  (bf16 side tensors, 16 B aligned): each epilogue warp moves 32 rows x 64 columns at a time through its own
-//           XOR-swizzled shared-memory staging blocks — global loads of res/cx/aux and stores of out/out2 are full
-//           128 B row segments (4 rows per warp instruction), the thread-per-row TMEM layout only ever touches smem.
+//           XOR-swizzled shared-memory staging blocks — the res/cx/aux blocks arrive as TMA boxes one item ahead, stores of
+//           out/out2 are full 128 B row segments (4 rows per warp instruction), the thread-per-row TMEM layout only ever
+//           touches smem.  The feature set is a compile-time mask (staged_epilogue<BN, MASK, CTAS>).
 //   direct  : thread-per-row 16 B vectors straight to global (fp32 outputs such as dW accumulation, unaligned shapes).
 #include "dx_gemm_epilogue.cuh"
 #include <cudaTypedefs.h>
@@ -250,25 +254,6 @@ __device__ __forceinline__ void stage_store(uint32_t buf, void* base, long long 
                    : "r"(sp + i * 512 + ((i & 1) ? po : pe)));
       *reinterpret_cast<uint4*>(gp + i * gstep) = u;
     }
-  }
-}
-// asynchronous variant of stage_load (cp.async 16 B, zero-fill out of range): prefetch of the next super-chunk
-__device__ __forceinline__ void stage_load_async(uint8_t* buf, const void* base, long long ld, int m_base, int n0, int M, int N,
-                                                 int lane) {
-  const int piece = lane & 7, rsub = lane >> 3;
-  const int col = n0 + piece * 8;
-  const bool col_ok = col < N;
-  const bf16* gp = reinterpret_cast<const bf16*>(base) + (col_ok ? ((long long)(m_base + rsub) * ld + col) : 0);
-  const long long gstep = col_ok ? 4 * ld : 0;
-  const uint32_t sp = smem_u32(buf) + rsub * 128;
-  const uint32_t pe = (uint32_t)((piece ^ rsub) << 4), po = (uint32_t)((piece ^ (rsub + 4)) << 4);
-  const int rows = col_ok ? (M - m_base - rsub) : 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool ok = 4 * i < rows;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sp + i * 512 + ((i & 1) ? po : pe)),
-                 "l"(ok ? gp + i * gstep : gp), "r"(ok ? 16 : 0)
-                 : "memory");
   }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

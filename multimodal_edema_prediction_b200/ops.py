@@ -257,7 +257,8 @@ def _psi_groups(psi, B, T1, V, d):
     return psi.view(B * T1, V + 1, d)[:, :V, :].permute(1, 0, 2)
 
 
-def embed_fwd(xs, V, d, W0, b0, gamma, beta, run_mean, run_var, W4, b4, nobs, special, tab, act_dtype, training):
+def embed_fwd(xs, V, d, W0, b0, gamma, beta, run_mean, run_var, W4, b4, nobs, special, tab, act_dtype, training,
+              return_hidden=False):
     """psi[B,T+1,V+1,d] = embedding of the binned grid: stats -> hidden -> ONE grouped tensor-core GEMM over the V
     variables (64 -> d, written into the strided psi view) -> special-cell substitution."""
     B, T, _ = xs.shape
@@ -273,10 +274,12 @@ def embed_fwd(xs, V, d, W0, b0, gamma, beta, run_mean, run_var, W4, b4, nobs, sp
     psi = torch.empty((B, T + 1, V + 1, d), device=dev, dtype=act_dtype)
     gemm_(hn, cast(W4, act_dtype), out=_psi_groups(psi, B, T + 1, V, d), bias=b4, act_dtype=act_dtype)
     _call("dx_embed_special", _p(xs), B, T, V, d, _p(special), _p(tab), _p(psi), L.dtype_code(act_dtype))
+    if return_hidden:            # the backward's dW4 GEMM takes hn as an operand: keeping it saves one recomputation pass
+        return psi, mean, rstd, hn
     return psi, mean, rstd
 
 
-def embed_bwd(xs, V, d, W0, b0, gamma, beta, W4, nobs, mean, rstd, dpsi, grads, training):
+def embed_bwd(xs, V, d, W0, b0, gamma, beta, W4, nobs, mean, rstd, dpsi, grads, training, hn=None):
     """grads: dict with f32 tensors dW0, db0, dgamma, dbeta, dW4, db4, dnobs, dspecial (accumulated). Returns dtab [B,d].
     dpsi is consumed (its special cells are zeroed in place)."""
     B, T, _ = xs.shape
@@ -285,7 +288,8 @@ def embed_bwd(xs, V, d, W0, b0, gamma, beta, W4, nobs, mean, rstd, dpsi, grads, 
     _chk(dpsi)
     dtab = torch.empty((B, d), device=dev, dtype=torch.float32)
     _call("dx_embed_special_bwd", _p(xs), B, T, V, d, _p(dpsi), _dt(dpsi), _p(grads["dspecial"]), _p(dtab))
-    hn = _embed_hidden(xs, V, W0, b0, nobs, gamma, beta, mean, rstd, at)
+    if hn is None:
+        hn = _embed_hidden(xs, V, W0, b0, nobs, gamma, beta, mean, rstd, at)
     dv = _psi_groups(dpsi, B, T1, V, d)                                           # [V, B*T1, d]
     gemm_(dv, hn, a_mn=True, b_mn=True, out=grads["dW4"], accumulate=True)         # dW4[v] += dout_v^T hn_v
     colsum(dpsi.view(B * T1, (V + 1) * d)[:, :V * d], grads["db4"].view(-1), accumulate=True)

@@ -227,7 +227,8 @@ def _embed(xs, V, d, W0, b0, gamma, beta, W4, b4, nobs, special, tab, mean, rstd
     return psi, mean, rstd, h
 
 
-def embed_fwd(xs, V, d, W0, b0, gamma, beta, run_mean, run_var, W4, b4, nobs, special, tab, act_dtype, training):
+def embed_fwd(xs, V, d, W0, b0, gamma, beta, run_mean, run_var, W4, b4, nobs, special, tab, act_dtype, training,
+              return_hidden=False):
     if training:
         psi, mean, rstd, h = _embed(xs, V, d, W0, b0, gamma, beta, W4, b4, nobs, special, tab, None, None)
         if run_mean is not None:
@@ -238,10 +239,12 @@ def embed_fwd(xs, V, d, W0, b0, gamma, beta, run_mean, run_var, W4, b4, nobs, sp
     else:
         mean, rstd = run_mean.clone(), torch.rsqrt(run_var + 1e-5)
         psi, _, _, _ = _embed(xs, V, d, W0, b0, gamma, beta, W4, b4, nobs, special, tab, mean, rstd)
+    if return_hidden:
+        return psi.to(act_dtype).contiguous(), mean.contiguous(), rstd.contiguous(), None
     return psi.to(act_dtype).contiguous(), mean.contiguous(), rstd.contiguous()
 
 
-def embed_bwd(xs, V, d, W0, b0, gamma, beta, W4, nobs, mean, rstd, dpsi, grads, training):
+def embed_bwd(xs, V, d, W0, b0, gamma, beta, W4, nobs, mean, rstd, dpsi, grads, training, hn=None):
     B = xs.shape[0]
     with torch.enable_grad():
         leaves = [t.detach().clone().requires_grad_(True) for t in (W0, b0, gamma, beta, W4)]
