@@ -433,3 +433,39 @@ def test_attention_dropout_fwd_bwd(ops, dt, S, D, H):
     rq, rk, rv = torch.empty(B, S, D), torch.empty(B, S, D), torch.empty(B, S, D)
     E.attn_bwd(*cpu(q, k, v, o, go, lse), H, rq, rk, rv, drop)
     assert rel(dqkv, torch.cat([rq, rk, rv], 2)) < TOL[dt] * 2
+
+
+@pytest.mark.parametrize("M,N,K", [(520, 392, 1160), (136, 256, 2056), (1000, 520, 1096), (264, 264, 1032)])
+def test_gemm_cta_pair_ragged_shapes(ops, monkeypatch, M, N, K):
+    """CTA-pair (cluster of 2, tcgen05.mma.cta_group::2) kernel on shapes whose last 256-row tile is partly or (for the
+    second CTA) wholly outside the matrix, N tails, and every operand layout that has a pair instance: staged epilogues with
+    K-major and MN-major B, and the fp32-accumulating dW form — forced on (DX_GEMM_PAIR=1) and against the single-CTA
+    kernel (DX_GEMM_PAIR=0) and the emulator."""
+    bf = torch.bfloat16
+    a, b = rnd(M, K, dtype=bf, seed=90), rnd(N, K, dtype=bf, seed=91, scale=0.1)
+    bt = b.t().contiguous()                                   # [K,N]: MN-major B
+    bias, rs = rnd(N, seed=92), torch.rand(M, device="cuda") + 0.5
+    res = rnd(M, N, dtype=bf, seed=93)
+    at_, bt_ = rnd(K, M, dtype=bf, seed=94), rnd(K, N, dtype=bf, seed=95, scale=0.1)    # dW form: A^T B over K rows
+
+    def run():
+        o1, o1b = torch.empty(M, N, device="cuda", dtype=bf), torch.empty(M, N, device="cuda", dtype=bf)
+        ops.gemm_(a, b, out=o1, out2=o1b, row_scale=rs, bias=bias, act=ops.ACT_GELU, act_dtype=bf)
+        o2, rq = torch.empty(M, N, device="cuda", dtype=bf), torch.zeros(M, device="cuda")
+        ops.gemm_(a, bt, b_mn=True, out=o2, res=res, row_sumsq=rq, act_dtype=bf)
+        o3 = torch.ones(M, N, device="cuda")
+        ops.gemm_(at_, bt_, a_mn=True, b_mn=True, out=o3, accumulate=True)
+        return o1, o1b, o2, rq, o3
+
+    monkeypatch.setenv("DX_GEMM_PAIR", "1")
+    pair = run()
+    monkeypatch.setenv("DX_GEMM_PAIR", "0")
+    single = run()
+    for p_, s_ in zip(pair, single):
+        assert rel(p_, s_) < 1e-5          # same bf16 products, fp32 accumulation: only the summation order differs
+    r1, r1b = torch.empty(M, N), torch.empty(M, N)
+    E.gemm_(*cpu(a, b), out=r1, out2=r1b, row_scale=rs.cpu(), bias=bias.cpu(), act=ops.ACT_GELU)
+    assert rel(pair[0], r1) < TOL[bf] and rel(pair[1], r1b) < TOL[bf]
+    r3 = torch.ones(M, N)
+    E.gemm_(*cpu(at_, bt_), a_mn=True, b_mn=True, out=r3, accumulate=True)
+    assert rel(pair[4], r3) < 1e-4
