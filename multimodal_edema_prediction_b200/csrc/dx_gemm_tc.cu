@@ -125,6 +125,23 @@ __device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* m
       ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// TMA load written into the same shared-memory offset of every CTA in `mask` (and counted on each one's mbarrier at the same
+// offset): two CTAs working on different M tiles of the same N tile fetch each half of the B block from L2 only once
+__device__ __forceinline__ void tma_load_3d_mcast(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                  uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], "
+      "[%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+// single-CTA MMAs, but the completion is signalled on the barrier at this offset in BOTH CTAs of the cluster
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -334,18 +351,19 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
   bool side_loaded = false, bias_loaded = false;   // the current item's loads were issued while the previous item ran
   uint32_t tcount = 0;
   // CTA pair: both CTAs walk the same 256-row tiles; this CTA owns rows [rank*128, +128) of each
-  const int m_off = CTAS == 2 ? (int)cluster_ctarank() * BM : 0;
-  const int ustep = (int)gridDim.x / CTAS;
+  constexpr int CL = CTAS == 1 ? 1 : 2;   // CTAs per cluster (CTAS: 1 single, 2 cta_group::2 pair, 3 B-multicast pair)
+  const int m_off = CL == 2 ? (int)cluster_ctarank() * BM : 0;
+  const int ustep = (int)gridDim.x / CL;
   const uint32_t empty_remote = CTAS == 2 ? mapa_u32(smem_u32(tmem_empty_bar), 0) : 0;   // the leader's tmem_empty_bar[0]
   // the staged epilogue never runs with split-K (work unit == tile); each tile's coordinates are decoded once, one tile
   // ahead (integer divisions), and serve both the cross-tile prefetch and the next iteration
   int mi = 0, ni = 0, z = 0;
-  if ((int)blockIdx.x / CTAS < p.total_tiles) tile_decode(p, (int)blockIdx.x / CTAS, mi, ni, z);
-  for (int unit = (int)blockIdx.x / CTAS; unit < p.total_tiles; unit += ustep, ++tcount) {
+  if ((int)blockIdx.x / CL < p.total_tiles) tile_decode(p, (int)blockIdx.x / CL, mi, ni, z);
+  for (int unit = (int)blockIdx.x / CL; unit < p.total_tiles; unit += ustep, ++tcount) {
     int mi2 = 0, ni2 = 0, z2 = -1;
     if (unit + ustep < p.total_tiles) tile_decode(p, unit + ustep, mi2, ni2, z2);
     const int n0 = ni * BN;
-    const int m0 = mi * (BM * CTAS) + m_off;
+    const int m0 = mi * (BM * CL) + m_off;
     const uint32_t slot = tcount & 1, use = tcount >> 1;
     const uint32_t acc = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
     DxEpi e = e0;
@@ -374,7 +392,7 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
         } else {
           if (z2 == z) {   // next tile exists and lies in the same batch slice: the pointers of `e` are valid for it
             nc2 = ni2 * BN + chalf * 64;
-            m_base2 = mi2 * (BM * CTAS) + m_off + q * 32;
+            m_base2 = mi2 * (BM * CL) + m_off + q * 32;
             next = nc2 < e.N;
           }
         }
@@ -480,7 +498,14 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
   // leader (cluster rank 0).  Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), so the L2 -> SM
   // operand traffic per FLOP drops by a third against 128 x BN single-CTA tiles; each CTA's TMEM holds its 128 accumulator
   // rows and its own epilogue warps drain them.
-  constexpr int BNL = BN / CTAS;   // B rows staged by this CTA
+  // CTAS == 3: the same cluster of two, but each CTA runs its own 128 x BN MMAs (cta_group::1) on its own M tile; the two
+  // tiles share the N tile, and each CTA fetches HALF of the B block and multicasts it into both CTAs' rings.  This is the
+  // mode of the HBM-bound shapes (K <= 1024, N = dim): their L2 -> SM traffic (B re-read by every M tile) sat at the L2
+  // throughput cap.
+  constexpr bool PAIR = CTAS == 2, MC = CTAS == 3;
+  constexpr int CL = CTAS == 1 ? 1 : 2;
+  constexpr int BNL = PAIR ? BN / 2 : BN;   // B rows held in this CTA's ring
+  constexpr int BNH = BN / 2;               // B rows FETCHED by this CTA in the two cluster modes
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BNL * BK * 2;
   constexpr int TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);   // allocation must be a power of two
@@ -500,25 +525,25 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + BK - 1) / BK;
-  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0;
-  const int unit0 = (int)blockIdx.x / CTAS, ustep = (int)gridDim.x / CTAS;
+  const uint32_t cta_rank = CL == 2 ? cluster_ctarank() : 0;
+  const int unit0 = (int)blockIdx.x / CL, ustep = (int)gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, 1);
+      mbar_init(empty_bar + s, MC ? 2 : 1);   // B-multicast pair: both CTAs' MMAs must have released the stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full_bar + s, 1);
-      mbar_init(tmem_empty_bar + s, NEPI * CTAS);   // one arrival per epilogue warp (of both CTAs of a pair)
+      mbar_init(tmem_empty_bar + s, NEPI * (PAIR ? 2 : 1));   // one arrival per epilogue warp (of both CTAs of a pair)
     }
     for (int s = 0; s < 2 * NEPI; ++s) mbar_init(side_full_bar + s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    if (CTAS == 2) {
+    if (PAIR) {
       tmem_alloc_pair(tmem_slot, TMEM_COLS);
       tmem_relinquish_pair();
     } else {
@@ -527,7 +552,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     }
   }
   tc_fence_before();
-  if (CTAS == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything is signalled remotely
+  if (CL == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything is signalled remotely
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -536,13 +561,13 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     if (lane == 0) {
       // ===== TMA producer =====
       uint32_t it = 0;   // running k-block counter across tiles
-      const uint32_t leader_full = CTAS == 2 ? mapa_u32(smem_u32(full_bar), 0) : 0;
+      const uint32_t leader_full = PAIR ? mapa_u32(smem_u32(full_bar), 0) : 0;
       for (int unit = unit0; unit < p.total_tiles; unit += ustep) {
         const int tile = unit / p.splits, split = unit - tile * p.splits;
         int mi, ni, z;
         tile_decode(p, tile, mi, ni, z);
-        const int n0 = ni * BN + (int)cta_rank * BNL;
-        const int m0 = mi * (BM * CTAS) + (int)cta_rank * BM;
+        const int n0 = ni * BN + (PAIR ? (int)cta_rank * BNL : 0);
+        const int m0 = mi * (BM * CL) + (int)cta_rank * BM;
         const int kb_lo = split * p.kb_per_split, kb_hi = min(num_kb, kb_lo + p.kb_per_split);
         for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % STAGES;
@@ -551,7 +576,25 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const int k0 = kb * BK;
-          if (CTAS == 2) {
+          if (MC) {
+            // own A tile locally; own half of the B block into BOTH CTAs (the other half arrives from the peer)
+            mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_3d(sa, &tmA, full_bar + s, k0, m0, z);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_3d(sa + c * 8192, &tmA, full_bar + s, m0 + c * 64, k0, z);
+            }
+            if (!B_MN) {
+              tma_load_3d_mcast(sb + cta_rank * (BNH * BK * 2), &tmB, full_bar + s, k0, n0 + (int)cta_rank * BNH, z, 3);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BNH / 64; ++c) {
+                const int cc = (int)cta_rank * (BNH / 64) + c;
+                tma_load_3d_mcast(sb + cc * 8192, &tmB, full_bar + s, n0 + cc * 64, k0, z, 3);
+              }
+            }
+          } else if (PAIR) {
             // both CTAs' bytes are counted on the leader's barrier (its MMA thread consumes both halves)
             if (cta_rank == 0) mbar_arrive_expect_tx(full_bar + s, 2 * STAGE_BYTES);
             const uint32_t lb = leader_full + s * 8;
@@ -586,12 +629,12 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && cta_rank == 0) {
+    if (lane == 0 && (cta_rank == 0 || !PAIR)) {
       // ===== MMA issuer (the leader CTA of a pair issues for both) =====
       // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
       // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CTAS) >> 4) << 24);
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * (PAIR ? 2 : 1)) >> 4) << 24);
       uint32_t it = 0, tcount = 0;
       for (int unit = unit0; unit < p.total_tiles; unit += ustep, ++tcount) {
         const int split = unit % p.splits;
@@ -613,15 +656,16 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
             // MN-major: advance 16 k-rows = two 1024 B swizzle atoms.
             const uint64_t ad = make_smem_desc(sa + (A_MN ? k * 2048 : k * 32), p.a_lbo, p.a_sbo);
             const uint64_t bd = make_smem_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
-            if (CTAS == 2) umma_f16_pair(acc, ad, bd, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+            if (PAIR) umma_f16_pair(acc, ad, bd, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
             else umma_f16(acc, ad, bd, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
-          if (CTAS == 2) umma_commit_pair(empty_bar + s);
+          if (PAIR) umma_commit_pair(empty_bar + s);
+          else if (MC) umma_commit_mcast(empty_bar + s);
           else umma_commit(empty_bar + s);
         }
         // accumulator complete
-        if (CTAS == 2) umma_commit_pair(tmem_full_bar + slot);
+        if (PAIR) umma_commit_pair(tmem_full_bar + slot);
         else umma_commit(tmem_full_bar + slot);
       }
     }
@@ -660,7 +704,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
         int mi, ni, z;
         tile_decode(p, tile, mi, ni, z);
         const int n0 = ni * BN;
-        const int m0 = mi * (BM * CTAS) + (int)cta_rank * BM;
+        const int m0 = mi * (BM * CL) + (int)cta_rank * BM;
         const uint32_t slot = tcount & 1, use = tcount >> 1;
         const uint32_t acc = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
         DxEpi e = e0;
@@ -698,9 +742,12 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     }
   }
   tc_fence_before();
-  if (CTAS == 2) {
-    cluster_sync_all();   // the peer may still be reading this CTA's operands / signalling its barriers
-    if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  if (CL == 2) {
+    cluster_sync_all();   // the peer may still be reading this CTA's operands / signalling its barriers / writing its ring
+    if (warp == 1) {
+      if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+      else tmem_dealloc(tmem_base, TMEM_COLS);
+    }
   } else {
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -747,7 +794,8 @@ int make_tmap(CUtensorMap* map, const void* base, long long inner, long long out
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED, int CTAS = 1>
 int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr,
                const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
-  const int smem = STAGES * (BM * BK * 2 + (BN / CTAS) * BK * 2) + 1024 /*align slack*/ + 512 /*barriers*/ +
+  constexpr int CL = CTAS == 1 ? 1 : 2;
+  const int smem = STAGES * (BM * BK * 2 + (CTAS == 2 ? BN / 2 : BN) * BK * 2) + 1024 /*align slack*/ + 512 /*barriers*/ +
                    (STAGED ? NEPI * (p.stage_bufs * STG_BYTES + 512) : 0);
   if (smem > 232448) {
     dx_set_error("dx_gemm_tc: tile config BN=%d stages=%d needs %d B of shared memory", BN, STAGES, smem);
@@ -761,7 +809,7 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   }
   TcParams pp = p;
   pp.tiles_n = dx_ceil_div(d->N, BN);
-  pp.tiles_m = dx_ceil_div(d->M, BM * CTAS);
+  pp.tiles_m = dx_ceil_div(d->M, BM * CL);
   pp.raster_m = pp.tiles_m < pp.tiles_n ? 1 : 0;
   if (const char* env = getenv("DX_GEMM_RASTER_M")) pp.raster_m = atoi(env) != 0;
   long long total = (long long)pp.tiles_n * pp.tiles_m * (d->batch > 1 ? d->batch : 1);
@@ -776,7 +824,7 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   const int num_kb = dx_ceil_div(d->K, BK);
   const bool pure_acc = d->accumulate && d->out_dtype == DX_F32 && !d->out2 && !d->res && !d->aux && !d->cx && !d->bias &&
                         !d->row_scale && !d->row_sumsq && !d->row_dot && d->act == DX_ACT_NONE;
-  const int workers = num_sms / CTAS;   // CTAs, or CTA pairs
+  const int workers = num_sms / CL;   // CTAs, or CTA pairs
   const double eff1 = (double)total / ((double)((total + workers - 1) / workers) * workers);   // wave efficiency unsplit
   if (!STAGED && pure_acc && eff1 < 0.85 && num_kb >= 64) {
     // smallest split whose work units fill >= 85 % of whole waves (atomic traffic grows with the split), else the best
@@ -796,7 +844,7 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
     return DX_ERR_ARG;
   }
   pp.total_tiles = (int)total;
-  if (CTAS == 2) {
+  if (CL == 2) {
     // one CTA pair (cluster of 2 = the two SMs of a TPC) per 256-row tile; persistent over min(pairs, tiles)
     const int pairs = (int)(total < workers ? total : workers);
     cudaLaunchConfig_t cfg = {};
@@ -828,6 +876,14 @@ constexpr bool pair_instantiated() { return (!A_MN && STAGED) || (A_MN && B_MN &
 template <bool A_MN, bool B_MN, bool STAGED>
 int launch_major(const dx_gemm_desc* d, int bn, int stages, int ctas, const CUtensorMap& ta, const CUtensorMap& tb,
                  const CUtensorMap& tr, const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
+  if (ctas == 3) {   // B-multicast cluster of two single-CTA MMAs: HBM-bound staged shapes
+    if constexpr (!A_MN && STAGED) {
+      if (bn == 256 && stages == 3) return launch_cfg<256, 3, A_MN, B_MN, STAGED, 3>(d, ta, tb, tr, tx, p, e, stream);
+      if (bn == 256 && stages == 2) return launch_cfg<256, 2, A_MN, B_MN, STAGED, 3>(d, ta, tb, tr, tx, p, e, stream);
+    }
+    dx_set_error("dx_gemm_tc: no B-multicast instance for BN=%d stages=%d a_mn=%d staged=%d", bn, stages, (int)A_MN, (int)STAGED);
+    return DX_ERR_UNSUPPORTED;
+  }
   if (ctas == 2) {
     if constexpr (pair_instantiated<A_MN, B_MN, STAGED>()) {
       if (bn == 256 && stages == 6) return launch_cfg<256, 6, A_MN, B_MN, STAGED, 2>(d, ta, tb, tr, tx, p, e, stream);
@@ -843,10 +899,12 @@ int launch_major(const dx_gemm_desc* d, int bn, int stages, int ctas, const CUte
   if (bn == 256 && stages == 2) return launch_cfg<256, 2, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
   if (bn == 192 && stages == 4) return launch_cfg<192, 4, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
   if (bn == 192 && stages == 3) return launch_cfg<192, 3, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
+  if (bn == 128 && stages == 2) return launch_cfg<128, 2, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
   if (bn == 128 && stages == 3) return launch_cfg<128, 3, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
   if (bn == 128 && stages == 4) return launch_cfg<128, 4, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
   if (bn == 128 && stages == 6) return launch_cfg<128, 6, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
   if (bn == 64 && stages == 4) return launch_cfg<64, 4, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
+  if (bn == 64 && stages == 6) return launch_cfg<64, 6, A_MN, B_MN, STAGED>(d, ta, tb, tr, tx, p, e, stream);
   dx_set_error("dx_gemm_tc: unsupported tile config BN=%d stages=%d", bn, stages);
   return DX_ERR_UNSUPPORTED;
 }
@@ -903,14 +961,21 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
     bn = d->N <= 64 ? 64 : (d->N >= 256 ? 256 : 128);
     // narrow outputs whose last 256-column tile would be half empty (N = 384: QKV with 2 heads of 64) use 128x192 tiles
     if (d->N > 128 && d->N < 1024 && (d->N % 256) > 128 && (d->N % 256) <= 192 && (d->N % 192) == 0) bn = 192;
+    // a single 128-wide column of few M tiles leaves most SMs idle (do = dx1 Wo on the time axis: 66 tiles): two 64-wide
+    // tiles per M block double the CTAs; the second one finds the A rows in L2
+    if (bn == 128 && d->N == 128 && (long long)dx_ceil_div(d->M, BM) * batch * 2 <= 160) bn = 64;
     const int stage_bytes = (BM + bn) * BK * 2;
-    const int cand[4][3] = {{4, 4, 4}, {6, 4, 3}, {4, 3, 2}, {4, 3, 3}};
+    const int cand[4][3] = {{6, 4, 4}, {6, 4, 3}, {4, 3, 2}, {4, 3, 3}};   // 64-wide tiles stream A: the deeper ring keeps more bytes in flight
     const int* c = cand[bn == 64 ? 0 : (bn == 128 ? 1 : (bn == 256 ? 2 : 3))];
     stages = 0;
     for (int i = 0; i < 3; ++i)
       if (c[i] * stage_bytes <= budget) { stages = c[i]; break; }
     if (stages || ring == 1) {
       if (!stages) stages = c[2];   // reported as unsupported by launch_cfg
+      if (const char* env = getenv("DX_GEMM_FORCE_STAGES")) {   // experiments
+        const int fs = atoi(env);
+        if (fs > 0) stages = fs;
+      }
       break;
     }
   }
@@ -931,11 +996,19 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
       if (st2) { ctas = 2; stages = st2; }
     }
   }
+  // B-multicast cluster for the HBM-bound staged shapes (shallow K, many M tiles re-reading the same B block).  Measured
+  // on B200: it removes a quarter of their L2 -> SM traffic (2.29 -> 1.72 GB per launch) but not a microsecond of their
+  // time (dX 187.4 us either way), i.e. those kernels are not bound by L2 throughput; it stays opt-in (DX_GEMM_MCAST=1,
+  // covered by the kernel tests) and off by default.
+  if (ctas == 1 && !user_cfg && staged && !d->a_mn && bn == 256 && batch == 1 && (stages == 3 || stages == 2)) {
+    if (const char* env = getenv("DX_GEMM_MCAST"))
+      if (atoi(env) == 1) ctas = 3;
+  }
   CUtensorMap ta, tb;
   if (!d->a_mn) rc = make_tmap(&ta, d->A, d->K, d->M, d->lda, batch, d->a_bs, BK, BM);
   else rc = make_tmap(&ta, d->A, d->M, d->K, d->lda, batch, d->a_bs, 64, BK);
   if (rc) return rc;
-  if (!d->b_mn) rc = make_tmap(&tb, d->B, d->K, d->N, d->ldb, batch, d->b_bs, BK, bn / ctas);
+  if (!d->b_mn) rc = make_tmap(&tb, d->B, d->K, d->N, d->ldb, batch, d->b_bs, BK, ctas == 1 ? bn : bn / 2);
   else rc = make_tmap(&tb, d->B, d->N, d->K, d->ldb, batch, d->b_bs, 64, BK);
   if (rc) return rc;
   TcParams p;

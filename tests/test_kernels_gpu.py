@@ -469,3 +469,28 @@ def test_gemm_cta_pair_ragged_shapes(ops, monkeypatch, M, N, K):
     r3 = torch.ones(M, N)
     E.gemm_(*cpu(at_, bt_), a_mn=True, b_mn=True, out=r3, accumulate=True)
     assert rel(pair[4], r3) < 1e-4
+
+
+def test_gemm_b_multicast_cluster_mode(ops, monkeypatch):
+    """Opt-in cluster mode of the staged kernels (two single-CTA MMAs on neighbouring M tiles, each CTA fetching half of the
+    B block and TMA-multicasting it into both rings): same results as the default kernel, K-major and MN-major B."""
+    bf = torch.bfloat16
+    M, N, K = 1000, 520, 264
+    a, b = rnd(M, K, dtype=bf, seed=96), rnd(N, K, dtype=bf, seed=97, scale=0.1)
+    bt = b.t().contiguous()
+    res, cx = rnd(M, N, dtype=bf, seed=98), rnd(M, N, dtype=bf, seed=99)
+    num, den, bias = rnd(M, seed=100), torch.rand(M, device="cuda") + 1, rnd(N, seed=101)
+
+    def run():
+        o1, rq = torch.empty(M, N, device="cuda", dtype=bf), torch.zeros(M, device="cuda")
+        ops.gemm_(a, b, out=o1, bias=bias, res=res, row_sumsq=rq, act_dtype=bf)
+        o2 = torch.empty(M, N, device="cuda", dtype=bf)
+        ops.gemm_(a, bt, b_mn=True, out=o2, res=res, cx=cx, coef_num=num, coef_den=den, act_dtype=bf)
+        return o1, rq, o2
+
+    monkeypatch.setenv("DX_GEMM_MCAST", "1")
+    mc = run()
+    monkeypatch.setenv("DX_GEMM_MCAST", "0")
+    base = run()
+    for x, y in zip(mc, base):
+        assert rel(x, y) < 1e-5
