@@ -961,9 +961,6 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
     bn = d->N <= 64 ? 64 : (d->N >= 256 ? 256 : 128);
     // narrow outputs whose last 256-column tile would be half empty (N = 384: QKV with 2 heads of 64) use 128x192 tiles
     if (d->N > 128 && d->N < 1024 && (d->N % 256) > 128 && (d->N % 256) <= 192 && (d->N % 192) == 0) bn = 192;
-    // a single 128-wide column of few M tiles leaves most SMs idle (do = dx1 Wo on the time axis: 66 tiles): two 64-wide
-    // tiles per M block double the CTAs; the second one finds the A rows in L2
-    if (bn == 128 && d->N == 128 && (long long)dx_ceil_div(d->M, BM) * batch * 2 <= 160) bn = 64;
     const int stage_bytes = (BM + bn) * BK * 2;
     const int cand[4][3] = {{6, 4, 4}, {6, 4, 3}, {4, 3, 2}, {4, 3, 3}};   // 64-wide tiles stream A: the deeper ring keeps more bytes in flight
     const int* c = cand[bn == 64 ? 0 : (bn == 128 ? 1 : (bn == 256 ? 2 : 3))];
