@@ -163,6 +163,7 @@ class FusedAdamW:
     def step(self, grad_scale=1.0, lr=None):
         self.step_count += 1
         self.step_dev.add_(1)
+        ops.advance_drop_step()      # dropout sites add this device counter to their seeds: fresh masks on a replayed graph
         lr = self.lr if lr is None else lr
         clip = None
         if self.max_grad_norm is not None:
