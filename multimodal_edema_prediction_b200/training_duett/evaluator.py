@@ -57,47 +57,42 @@ def evaluate_binary(model, loader, device, forward_fn):
     return binary_metrics(torch.cat(logits_all), torch.cat(y_all))
 
 
-def make_teacher_forward():
-    """Main-head evaluation: dict output -> main_logit, legacy tuple -> [0], tensor -> itself."""
+def _main_logit(out):
+    """Teacher output -> main-head logits: dict (pathology modes) -> "main_logit", legacy tuple -> first entry."""
+    if isinstance(out, dict):
+        return out["main_logit"]
+    return out[0] if isinstance(out, tuple) else out
+
+
+def _aux_logit(out):
+    if not isinstance(out, tuple):
+        raise RuntimeError("aux forward is only available with TeacherModel(use_aux_cxr=True)")
+    return out[1]
+
+
+def _make_forward(with_image: bool, pick):
+    """forward_fn factory for evaluate_binary: moves the collate-format batch, runs the model, picks the scored logits."""
     from .engine import _move_lists
 
     @torch.no_grad()
-    def _fwd(teacher, batch, device):
+    def _fwd(model, batch, device):
         b = _move_lists(batch, device)
-        out = teacher(b["x_ts"], b["x_static"], b["bin_ends"], b["pixel_values"])
-        if isinstance(out, dict):
-            z = out["main_logit"]
-        elif isinstance(out, tuple):
-            z = out[0]
-        else:
-            z = out
-        return {"logits": z, "y": b["y"]}
+        inputs = (b["x_ts"], b["x_static"], b["bin_ends"]) + ((b["pixel_values"],) if with_image else ())
+        return {"logits": pick(model(*inputs)), "y": b["y"]}
 
     return _fwd
+
+
+def make_teacher_forward():
+    """Main-head evaluation of a teacher (training_duett/evaluator.py:40-60)."""
+    return _make_forward(True, _main_logit)
 
 
 def make_teacher_aux_forward():
-    """Auxiliary CXR-only head; only valid when the teacher returns a tuple (use_aux_cxr=True)."""
-    from .engine import _move_lists
-
-    @torch.no_grad()
-    def _fwd(teacher, batch, device):
-        b = _move_lists(batch, device)
-        out = teacher(b["x_ts"], b["x_static"], b["bin_ends"], b["pixel_values"])
-        if not isinstance(out, tuple):
-            raise RuntimeError("aux forward is only available with TeacherModel(use_aux_cxr=True)")
-        return {"logits": out[1], "y": b["y"]}
-
-    return _fwd
+    """Auxiliary CXR-only head; valid only when the teacher returns a tuple (training_duett/evaluator.py:63-76)."""
+    return _make_forward(True, _aux_logit)
 
 
 def make_student_forward():
-    from .engine import _move_lists
-
-    @torch.no_grad()
-    def _fwd(student, batch, device):
-        b = _move_lists(batch, device)
-        z = student(b["x_ts"], b["x_static"], b["bin_ends"])
-        return {"logits": z, "y": b["y"]}
-
-    return _fwd
+    """Student evaluation (training_duett/evaluator.py:79-88)."""
+    return _make_forward(False, lambda z: z)
