@@ -96,3 +96,92 @@ def make_teacher_aux_forward():
 def make_student_forward():
     """Student evaluation (training_duett/evaluator.py:79-88)."""
     return _make_forward(False, lambda z: z)
+
+
+def _bce_mean(logits: torch.Tensor, y: torch.Tensor) -> float:
+    """mean of max(l,0) - l*y + log1p(exp(-|l|)) (training_duett/evaluator.py:181-183)."""
+    if logits.numel() == 0:
+        return float("nan")
+    l, t = logits.double(), y.double()
+    return float((l.clamp_min(0) - l * t + torch.log1p(torch.exp(-l.abs()))).mean())
+
+
+def _pearson(a: torch.Tensor, b: torch.Tensor) -> float:
+    """Population Pearson correlation, NaN for fewer than two samples or zero variance (evaluator.py:186-194)."""
+    if a.numel() < 2:
+        return float("nan")
+    a, b = a.double(), b.double()
+    da, db = a - a.mean(), b - b.mean()
+    va, vb = float((da * da).mean()), float((db * db).mean())
+    if va == 0 or vb == 0:
+        return float("nan")
+    return float((da * db).mean() / (va ** 0.5 * vb ** 0.5))
+
+
+@torch.no_grad()
+def evaluate_dual_pathology(model, loader, device, pathology_labels, *, query_ref=None) -> dict:
+    """Per-pathology evaluation of a (Patch)DualPathologyPerceiver teacher — same result dict as the reference's
+    training_duett/evaluator.py:197-335: for every label the masked AUROC / AUPRC of the image, time-series and fusion
+    branches with their gaps, per-branch BCE and delta, residual-correction usage and its correlation with the image
+    branch's error, beta; macro means as main_auroc / main_auprc.  Logits stay on the device (every rank sees the whole
+    loader, see binary_metrics); ranking runs in dx_binary_auc."""
+    from .engine import _move_lists
+
+    model.eval()
+    cols = {k: [] for k in ("img_logits", "ts_logits", "fusion_logits", "scaled_correction", "y", "mask")}
+    for batch in loader:
+        b = _move_lists(batch, device)
+        out = model(b["x_ts"], b["x_static"], b["bin_ends"], b["pixel_values"])
+        if not isinstance(out, dict) or "fusion_logits" not in out:
+            raise RuntimeError("evaluate_dual_pathology needs a dual_pathology_mode teacher")
+        for k in ("img_logits", "ts_logits", "fusion_logits"):
+            cols[k].append(out[k].detach().float())
+        if "scaled_correction" in out:
+            cols["scaled_correction"].append(out["scaled_correction"].detach().float())
+        cols["y"].append(b["y_multi"].float())
+        cols["mask"].append(b["y_multi_mask"].float())
+    K = len(pathology_labels)
+
+    def table(k):
+        t = torch.cat(cols[k])
+        return torch.stack([_gather_all(t[:, j].contiguous()) for j in range(K)], 1)
+
+    img, ts, fus, y, mk = (table(k) for k in ("img_logits", "ts_logits", "fusion_logits", "y", "mask"))
+    corr = table("scaled_correction") if cols["scaled_correction"] else None
+    unwrapped = model.module if hasattr(model, "module") else model
+    perceiver = getattr(unwrapped, "perceiver", None)
+    beta = perceiver.beta.detach().float().cpu() if perceiver is not None and hasattr(perceiver, "beta") else None
+    nan = float("nan")
+
+    def ranked(logits, yk):
+        if yk.numel() == 0:
+            return nan, nan
+        r = ops.binary_auc(logits, yk, apply_sigmoid=True).tolist()
+        return float(r[0]), float(r[1])
+
+    per_label = []
+    for k in range(K):
+        m = mk[:, k] > 0.5
+        yk = y[m, k].contiguous()
+        li, lt, lf = (t[m, k].contiguous() for t in (img, ts, fus))
+        (ai, ri), (at, rt), (af, rf) = ranked(li, yk), ranked(lt, yk), ranked(lf, yk)
+        ib, tb, fb = _bce_mean(li, yk), _bce_mean(lt, yk), _bce_mean(lf, yk)
+        if corr is not None and yk.numel():
+            ck = corr[m, k]
+            mean_abs_corr, corr_r = float(ck.abs().double().mean()), _pearson(ck, yk - torch.sigmoid(li.double()).float())
+        else:
+            mean_abs_corr, corr_r = nan, nan
+        per_label.append({
+            "name": pathology_labels[k], "n_valid": int(m.sum()), "pos_frac": float(yk.double().mean()) if yk.numel() else nan,
+            "img_auroc": ai, "ts_auroc": at, "fus_auroc": af, "gap_i2f": af - ai, "gap_t2f": af - at,
+            "img_auprc": ri, "ts_auprc": rt, "fus_auprc": rf, "gap_i2f_pr": rf - ri, "gap_t2f_pr": rf - rt,
+            "img_bce": ib, "ts_bce": tb, "fus_bce": fb, "delta_bce": fb - ib,
+            "mean_abs_corr": mean_abs_corr, "corr_residual": corr_r, "beta": float(beta[k]) if beta is not None else nan,
+        })
+
+    def macro(key):
+        vals = [r[key] for r in per_label if r[key] == r[key]]
+        return sum(vals) / len(vals) if vals else nan
+
+    return {"labels": list(pathology_labels), "n": int(y.shape[0]), "main_auroc": macro("fus_auroc"),
+            "main_auprc": macro("fus_auprc"), "per_label": per_label}

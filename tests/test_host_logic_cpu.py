@@ -247,3 +247,60 @@ def test_student_step_with_dropout_host_logic(emu):
         assert ops.DROP_LOG == []
     finally:
         ops.DROP_LOG = None
+
+
+def test_evaluate_dual_pathology_surface(emu):
+    """evaluate_dual_pathology: result keys and values against the reference's formulas restated with numpy / sklearn
+    (training_duett/evaluator.py:197-335) on a stub teacher; the ranking kernel is emulated by its contract."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from multimodal_edema_prediction_b200.training_duett import evaluator
+    K, labels = 3, ("a", "b", "c")
+    g = torch.Generator().manual_seed(3)
+
+    class Perc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.beta = torch.nn.Parameter(torch.tensor([0.5, 1.0, 1.5]))
+
+    class Teacher(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.perceiver = Perc()
+
+        def forward(self, x_ts, x_static, bin_ends, pv):
+            s = torch.stack([t.sum() for t in x_ts])[:, None]
+            img = pv[:, :K] + 0.1 * s
+            corr = 0.3 * pv[:, K:2 * K]
+            return {"img_logits": img, "ts_logits": pv[:, 2 * K:3 * K], "fusion_logits": img + corr, "scaled_correction": corr,
+                    "main_logit": img[:, 0]}
+
+    batches = []
+    for _ in range(4):
+        n = 9
+        batches.append({"x_ts": tuple(torch.randn(2, 3, generator=g) for _ in range(n)),
+                        "x_static": tuple(torch.zeros(1) for _ in range(n)), "bin_ends": tuple(torch.zeros(1) for _ in range(n)),
+                        "y": torch.zeros(n), "pixel_values": torch.randn(n, 3 * K, generator=g),
+                        "y_multi": (torch.rand(n, K, generator=g) < 0.4).float(),
+                        "y_multi_mask": (torch.rand(n, K, generator=g) < 0.8).float()})
+    model = Teacher()
+    res = evaluator.evaluate_dual_pathology(model, batches, torch.device("cpu"), labels)
+    outs = [model(b["x_ts"], b["x_static"], b["bin_ends"], b["pixel_values"]) for b in batches]
+    cat = lambda k: torch.cat([o[k] for o in outs]).detach().numpy()
+    img, fus, corr = cat("img_logits"), cat("fusion_logits"), cat("scaled_correction")
+    y = torch.cat([b["y_multi"] for b in batches]).numpy()
+    mk = torch.cat([b["y_multi_mask"] for b in batches]).numpy().astype(bool)
+    assert res["labels"] == list(labels) and res["n"] == 36 and len(res["per_label"]) == K
+    fa = []
+    for k in range(K):
+        m = mk[:, k]
+        yk, li, lf, ck = y[m, k], img[m, k], fus[m, k], corr[m, k]
+        r = res["per_label"][k]
+        sig = lambda z: 1.0 / (1.0 + np.exp(-z))
+        assert r["n_valid"] == int(m.sum()) and abs(r["pos_frac"] - yk.mean()) < 1e-12
+        assert abs(r["img_auroc"] - roc_auc_score(yk, sig(li))) < 1e-6 and abs(r["fus_auprc"] - average_precision_score(yk, sig(lf))) < 1e-6
+        bce = lambda l: float((np.maximum(l, 0) - l * yk + np.log1p(np.exp(-np.abs(l)))).mean())
+        assert abs(r["delta_bce"] - (bce(lf) - bce(li))) < 1e-6 and abs(r["mean_abs_corr"] - np.abs(ck).mean()) < 1e-6
+        assert abs(r["corr_residual"] - np.corrcoef(ck, yk - sig(li))[0, 1]) < 1e-5
+        assert abs(r["gap_i2f"] - (r["fus_auroc"] - r["img_auroc"])) < 1e-12 and abs(r["beta"] - [0.5, 1.0, 1.5][k]) < 1e-7
+        fa.append(r["fus_auroc"])
+    assert abs(res["main_auroc"] - sum(fa) / K) < 1e-12

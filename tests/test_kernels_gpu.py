@@ -3,6 +3,8 @@ torch contract in tests/ops_emulator.py, fp32 and bf16 storage.  Tolerances: fp3
 north-star bound is 1e-3), bf16 2e-2 (north-star bound)."""
 import math
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -494,3 +496,36 @@ def test_gemm_b_multicast_cluster_mode(ops, monkeypatch):
     base = run()
     for x, y in zip(mc, base):
         assert rel(x, y) < 1e-5
+
+
+def test_evaluate_dual_pathology_on_device(ops):
+    """evaluate_dual_pathology with the real ranking kernel: masked per-label AUROC / AUPRC against sklearn."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from multimodal_edema_prediction_b200.training_duett import evaluator
+    K = 3
+    g = torch.Generator().manual_seed(5)
+
+    class Teacher(torch.nn.Module):
+        def forward(self, x_ts, x_static, bin_ends, pv):
+            return {"img_logits": pv[:, :K], "ts_logits": pv[:, K:2 * K], "fusion_logits": pv[:, :K] + 0.3 * pv[:, 2 * K:],
+                    "scaled_correction": 0.3 * pv[:, 2 * K:]}
+
+    batches = []
+    for _ in range(5):
+        n = 40
+        batches.append({"x_ts": tuple(torch.zeros(1) for _ in range(n)), "x_static": tuple(torch.zeros(1) for _ in range(n)),
+                        "bin_ends": tuple(torch.zeros(1) for _ in range(n)), "y": torch.zeros(n),
+                        "pixel_values": torch.randn(n, 3 * K, generator=g), "y_multi": (torch.rand(n, K, generator=g) < 0.4).float(),
+                        "y_multi_mask": (torch.rand(n, K, generator=g) < 0.8).float()})
+    res = evaluator.evaluate_dual_pathology(Teacher().cuda(), batches, torch.device("cuda"), ("a", "b", "c"))
+    pv = torch.cat([b["pixel_values"] for b in batches]).numpy()
+    y = torch.cat([b["y_multi"] for b in batches]).numpy()
+    mk = torch.cat([b["y_multi_mask"] for b in batches]).numpy().astype(bool)
+    sig = lambda z: 1.0 / (1.0 + np.exp(-z))
+    for k in range(K):
+        m = mk[:, k]
+        r = res["per_label"][k]
+        assert r["n_valid"] == int(m.sum())
+        assert abs(r["ts_auroc"] - roc_auc_score(y[m, k], sig(pv[m, K + k]))) < 1e-6
+        assert abs(r["img_auprc"] - average_precision_score(y[m, k], sig(pv[m, k]))) < 1e-6
+    assert res["n"] == 200 and res["main_auroc"] == res["main_auroc"]
