@@ -110,3 +110,45 @@ def test_flat_param_order_follows_backward_completion():
     for p in flat.params:                       # parameters and grads are views into the flat buffers
         assert p.data_ptr() >= flat.data.data_ptr() and p.grad.data_ptr() >= flat.grad.data_ptr()
     assert flat.numel % 8 == 0
+
+
+def _eval_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _install_emulator()
+        from multimodal_edema_prediction_b200.training_duett import evaluator
+        g = torch.Generator().manual_seed(11)
+        z_all, y_all = torch.randn(37, generator=g), (torch.rand(37, generator=g) < 0.4).float()
+        lo, hi = (0, 23) if rank == 0 else (23, 37)                 # uneven shards
+        res = evaluator.binary_metrics(z_all[lo:hi], y_all[lo:hi])
+        q.put((rank, res))
+    except Exception as ex:
+        import traceback
+        q.put((rank, "error", traceback.format_exc(), repr(ex)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_evaluator_scores_the_whole_loader_on_every_rank_world2():
+    """binary_metrics gathers every rank's (unevenly sized) shard before ranking: both ranks report the AUROC / AUPRC of the
+    whole evaluation set (the reference scores rank 0's shard only)."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(11)
+    z_all, y_all = torch.randn(37, generator=g), (torch.rand(37, generator=g) < 0.4).float()
+    want_roc = roc_auc_score(y_all.numpy(), torch.sigmoid(z_all).numpy())
+    want_pr = average_precision_score(y_all.numpy(), torch.sigmoid(z_all).numpy())
+    for r in res:
+        assert r[1] != "error", r
+        rank, m = r
+        assert m["n"] == 37 and abs(m["auroc"] - want_roc) < 1e-12 and abs(m["auprc"] - want_pr) < 1e-12, (rank, m)
