@@ -1,0 +1,6 @@
+// Explicit instantiations of the tcgen05 GEMM launcher, group 2 (see DX_TC_GROUP_2 in dx_gemm_tc_impl.cuh).
+#include "dx_gemm_tc_impl.cuh"
+
+namespace dx_tc {
+DX_TC_GROUP_2(DX_TC_INSTANTIATE)
+}
