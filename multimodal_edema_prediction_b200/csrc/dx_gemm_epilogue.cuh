@@ -142,6 +142,26 @@ __device__ __forceinline__ void dx_epi_store(void* base, long long ld, int dtype
 struct DxRowConst {
   float rs, rs2, coef;
 };
+// Raw per-row operands of DxRowConst: loading them one tile ahead (and dividing only when the tile starts) keeps the
+// dependent global loads off the critical path of the persistent epilogue.
+struct DxRowRaw {
+  float rs, rs2, num, den;
+};
+__device__ __forceinline__ DxRowRaw dx_row_raw(const DxEpi& e, int m) {
+  DxRowRaw r;
+  r.rs = e.row_scale ? e.row_scale[m] : 1.f;
+  r.rs2 = e.row_scale2 ? e.row_scale2[m] : 1.f;
+  r.num = e.cx ? e.coef_num[m] : 0.f;
+  r.den = e.cx ? e.coef_den[m] : 1.f;
+  return r;
+}
+__device__ __forceinline__ DxRowConst dx_row_finish(const DxRowRaw& r) {
+  DxRowConst c;
+  c.rs = r.rs;
+  c.rs2 = r.rs2;
+  c.coef = r.num / fmaxf(r.den, 1e-24f);
+  return c;
+}
 __device__ __forceinline__ DxRowConst dx_row_const(const DxEpi& e, int m) {
   DxRowConst c;
   c.rs = e.row_scale ? e.row_scale[m] : 1.f;

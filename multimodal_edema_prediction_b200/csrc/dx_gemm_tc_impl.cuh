@@ -363,6 +363,8 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
   // the staged epilogue never runs with split-K (work unit == tile); each tile's coordinates are decoded once, one tile
   // ahead (integer divisions), and serve both the cross-tile prefetch and the next iteration
   int mi = 0, ni = 0, z = 0;
+  DxRowRaw raw_next{1.f, 1.f, 0.f, 1.f};
+  bool raw_ok = false;
   if ((int)blockIdx.x / CL < p.total_tiles) tile_decode(p, (int)blockIdx.x / CL, mi, ni, z);
   for (int unit = (int)blockIdx.x / CL; unit < p.total_tiles; unit += ustep, ++tcount) {
     int mi2 = 0, ni2 = 0, z2 = -1;
@@ -376,7 +378,14 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
     const int m_base = m0 + q * 32;
     const int m = m_base + lane;
     const bool row_ok = m < e.M;
-    const DxRowConst rc = row_ok ? dx_row_const(e, m) : DxRowConst{1.f, 1.f, 0.f};
+    // per-row constants: fetched one tile ahead when the next tile lies in the same batch slice
+    const DxRowConst rc = raw_ok ? dx_row_finish(raw_next) : (row_ok ? dx_row_const(e, m) : DxRowConst{1.f, 1.f, 0.f});
+    raw_ok = false;
+    if (z2 == z) {
+      const int mn = mi2 * (BM * CL) + m_off + q * 32 + lane;
+      raw_next = mn < e.M ? dx_row_raw(e, mn) : DxRowRaw{1.f, 1.f, 0.f, 1.f};
+      raw_ok = true;
+    }
     float rs = 0.f, rd = 0.f;
     const int nsc = min(BN / 64, (e.N - n0 + 63) / 64);
     bool acc_ready = false;
