@@ -54,13 +54,11 @@ def train_flops_per_sample(w=WORK):
 
 def synth_host_batch(B, seed, w=WORK, pin=True):
     """Collate-format batch on the host: tuples of per-sample tensors (duett/mimic_dataset.py:83,93-95)."""
-    from oracle import duett_oracle as O      # data generator only (synthetic inputs shared with the parity tests)
-    cfg = O.DuettConfig(d_static_num=w["d_static_num"], d_time_series_num=w["V"], n_timesteps=w["T"], d_embedding=w["d"],
-                        n_layers=w["L"], d_feedforward=w["d_ff"])
-    b = O.synth_batch(cfg, B, seed)
+    from multimodal_edema_prediction_b200.synth import synth_batch
+    b = synth_batch(w["d_static_num"], w["V"], w["T"], B, seed)
     if pin:
         b = {k: (tuple(t.pin_memory() for t in v) if isinstance(v, tuple) else v.pin_memory()) for k, v in b.items()}
-    return cfg, b
+    return b
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -74,7 +72,10 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     Bs = args.cpu_sample
-    cfg, b = synth_host_batch(Bs, 1234, pin=False)
+    w = WORK
+    cfg = O.DuettConfig(d_static_num=w["d_static_num"], d_time_series_num=w["V"], n_timesteps=w["T"], d_embedding=w["d"],
+                        n_layers=w["L"], d_feedforward=w["d_ff"])
+    b = synth_host_batch(Bs, 1234, pin=False)
     P = O.init_params(cfg, seed=0)
     Pl = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P.items()}
     xs, xt, tm, _ = O.feats_to_input(b["x_ts"], b["x_static"], b["bin_ends"], cfg.T)
@@ -190,7 +191,7 @@ def main():
     model, flat, opt, red = build(device, world)
     B = WORK["B"]
     nb = 4                                             # distinct synthetic batches, cycled
-    host = [synth_host_batch(B, 1234 + 17 * rank + i)[1] for i in range(nb)]
+    host = [synth_host_batch(B, 1234 + 17 * rank + i) for i in range(nb)]
     dev_batches = []
     for hb in host:
         x = model.feats_to_input((hb["x_ts"], hb["x_static"], list(hb["bin_ends"])), B)

@@ -1,6 +1,6 @@
 """BASELINE config 5 shape (T=128, V=512, d=256, L=2, heads 2 -> dh=128: SIMT attention path, 131k-wide time tokens) at a
 small batch: forward + backward through the nn.Module API in fp32 and bf16 modes on the GPU; checks finiteness and that
-the two precisions agree (bf16 bound).  usage: python tools/c5_smoke.py [B]"""
+the two precisions agree (bf16 bound).  usage: python tests/c5_smoke.py [B]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

@@ -1,7 +1,7 @@
 """Run-to-run determinism probe: the same student step (fwd + KD loss + bwd) N times on identical inputs; prints the largest
 relative deviation of tokens / logits / every gradient from run 0.  Atomic accumulation order gives ~1e-6 (fp32) or a few
 1e-3 (bf16 rounding flips); anything larger points at a race.
-usage: python tools/flake_check.py [N] [mode] [d] [L] [B]"""
+usage: python tests/flake_check.py [N] [mode] [d] [L] [B]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

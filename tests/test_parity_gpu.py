@@ -195,7 +195,7 @@ def _oracle_vs_cuda_student(cfg, B, mode, tol, seed=0, pool="mean"):
     losses = StudentKDLoss(kd_T=4.0, kd_alpha=0.5)(z, z_t.cuda(), batch["y"].cuda())
     # logits: the head's BatchNorm over B=4..16 samples amplifies the bf16 rounding of the pooled token ~10x (tokens above
     # agree to 5e-3) and the fp32 atomics of the row reductions make it vary run to run: 200 runs of the C1 case gave
-    # 0.030 / 0.048 / 0.066 (min / median / max, tools/flake_check.py with FLAKE_ORACLE=1), so bf16 gets 6 x tol.
+    # 0.030 / 0.048 / 0.066 (min / median / max, tests/flake_check.py with FLAKE_ORACLE=1), so bf16 gets 6 x tol.
     assert rel(z.cpu(), z_ref) < tol * (3 if mode == "fp32" else 6)
     assert rel(losses["total"].cpu(), L_ref["total"]) < tol
     losses["total"].backward()
