@@ -312,6 +312,19 @@ class Model(nn.Module):
     def feats_to_input(self, x, batch_size, limits=None):
         xs_ts, xs_static, times = x
         xs_ts, times = list(xs_ts), list(times)
+        augment = self.training and (self.aug_noise > 0 or self.aug_mask > 0) and not self.pretrain
+        if not augment and all(f.shape[0] <= self.max_len for f in xs_ts):
+            # plain batch (evaluation, SSL, KD student): no per-sample work on the host - the samples are stacked into
+            # the pinned staging buffer as they are and the all-zero mask column is appended on the device
+            n_timesteps = [len(ts) for ts in times]
+            pad_to = int(np.max(n_timesteps))
+            dev = self.device
+            if any(n != pad_to for n in n_timesteps):
+                xs_ts = [F.pad(t, (0, 0, 0, pad_to - t.shape[0])) for t in xs_ts]
+                times = [F.pad(t, (0, pad_to - t.shape[0])) for t in times]
+            raw = self._upload(xs_ts, "ts_raw", dev)
+            xs_ts = torch.cat((raw, raw.new_zeros(raw.shape[0], raw.shape[1], 1)), dim=2)
+            return self._upload(list(xs_static), "static", dev), xs_ts, self._upload(times, "times", dev), n_timesteps
         for i, f in enumerate(xs_ts):
             n_vars = f.shape[1] // 2
             if f.shape[0] > self.max_len:
