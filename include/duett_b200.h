@@ -215,10 +215,11 @@ int dx_fusion_logits_bwd(const float* d_img, const float* d_ts, const float* d_s
 /* Fused AdamW on flat f32 buffers + global-norm clipping pieces (training_duett/trainer.py:383,902; duett/duett.py:325-327;
  * duett/train_duett_ssl.py:191 gradient_clip_val).  Effective grad = g * grad_scale * (grad_scale_dev ? *grad_scale_dev : 1). */
 /* step_dev (int, device) overrides `step` and lr_scale_dev (float, device) multiplies lr when non-NULL, so a captured CUDA
- * graph of the whole training step stays valid as the step counter / LR schedule advance. */
+ * graph of the whole training step stays valid as the step counter / LR schedule advance.  shadow_bf16 (optional, n bf16
+ * elements): receives the updated parameters rounded to bf16 in the same pass (the tensor-core operands of the next step). */
 int dx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
              float weight_decay, int step, const float* grad_scale_dev, float grad_scale, const int* step_dev,
-             const float* lr_scale_dev, void* stream);
+             const float* lr_scale_dev, void* shadow_bf16, void* stream);
 int dx_sumsq(const float* x, int64_t n, float* out, void* stream);
 int dx_clip_factor(const float* sumsq, float max_norm, float* clip, void* stream);
 

@@ -37,7 +37,7 @@ SIGNATURES = {
     "dx_mean_rows_bwd": [P, P, I, I, I, L, I, P],
     "dx_gather_vec": [P, P, P, I, I, I, P],
     "dx_scatter_vec": [P, P, P, I, I, I, I, P],
-    "dx_adamw": [P, P, P, P, L, F, F, F, F, F, I, P, F, P, P, P],
+    "dx_adamw": [P, P, P, P, L, F, F, F, F, F, I, P, F, P, P, P, P],
     "dx_sumsq": [P, L, P, P],
     "dx_clip_factor": [P, F, P, P],
     "dx_sum_n": [P, I, P, L, I, P],

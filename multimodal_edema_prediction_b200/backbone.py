@@ -27,9 +27,15 @@ from .functional import BatchNorm2dFn, grad_sink, linear
 
 ENC_KEYS = ("g_attn", "wqkv", "wo", "g_ff", "w1", "b1", "w2", "b2", "g_final")
 
-# Set by ddp.GradReducer: called as hook("time_transformers.3") etc. from inside the backward as soon as an encoder's
-# parameter gradients are final, so its all-reduce bucket can start while the earlier layers are still running.
-GRAD_READY_HOOK = None
+# Registered by ddp.GradReducer.attach(): every hook is called as hook("time_transformers.3", ("w2", "b2", "g_final")) from
+# inside the backward as soon as those parameter gradients of that encoder are final (all kernels writing them are
+# enqueued), so their all-reduce bucket starts while the rest of the backward is still running.
+GRAD_READY_HOOKS = []
+
+
+def _notify(prefix, keys):
+    for h in GRAD_READY_HOOKS:
+        h(prefix, keys)
 
 
 class EncoderCtx:
@@ -38,7 +44,28 @@ class EncoderCtx:
                  "dim", "drop_attn", "drop_ff")
 
 
-def encoder_fwd(x, rowsq_x, B, S, dim, p, heads, d, keep=True, drop_p=0.0, tag=""):
+class ZeroPool:
+    """Zero-initialised f32 scratch handed out in slices: ONE memset for all the per-row accumulators (row norms, row dots,
+    split-K partial sums) of a whole forward or backward pass instead of a fill kernel per buffer."""
+
+    def __init__(self, numel, device):
+        self.buf = torch.zeros(max(int(numel), 1), device=device, dtype=torch.float32)
+        self.pos = 0
+
+    def take(self, n):
+        n8 = (int(n) + 7) // 8 * 8                      # slices stay 32 B aligned
+        if self.pos + n8 > self.buf.numel():            # never hand out unzeroed memory
+            return torch.zeros(int(n), device=self.buf.device, dtype=torch.float32)
+        out = self.buf[self.pos:self.pos + int(n)]
+        self.pos += n8
+        return out
+
+
+def _zeros(pool, n, dev):
+    return pool.take(n) if pool is not None else torch.zeros(n, device=dev, dtype=torch.float32)
+
+
+def encoder_fwd(x, rowsq_x, B, S, dim, p, heads, d, keep=True, drop_p=0.0, tag="", pool=None):
     """x: [B,S,dim] act tensor (dense), rowsq_x [B*S]. p: dict ENC_KEYS -> tensors (weights already in act dtype under
     'wqkv_c','wo_c','w1_c','w2_c'). Returns ctx with x2 / rowsq2 (un-normalised output + row norms)."""
     N = B * S
@@ -55,7 +82,7 @@ def encoder_fwd(x, rowsq_x, B, S, dim, p, heads, d, keep=True, drop_p=0.0, tag="
     drop_ff = (drop_p, ops.drop_seed(tag + ".ff", drop_p, (N, F))) if drop_p > 0 else None
     o, lse = ops.attn_fwd(q3[:, :, :d], q3[:, :, d:2 * d], q3[:, :, 2 * d:], heads, drop_attn)
     x1 = torch.empty((N, dim), device=dev, dtype=at)
-    rowsq1 = torch.zeros(N, device=dev, dtype=torch.float32)
+    rowsq1 = _zeros(pool, N, dev)
     ops.gemm_(o.view(N, d), p["wo_c"], out=x1, res=x2d, row_sumsq=rowsq1, act_dtype=at)
     s_f = ops.scalenorm_scale(rowsq1, p["g_ff"], dim)
     h = torch.empty((N, F), device=dev, dtype=at)
@@ -64,7 +91,7 @@ def encoder_fwd(x, rowsq_x, B, S, dim, p, heads, d, keep=True, drop_p=0.0, tag="
     if drop_ff:
         ops.dropout(h, drop_ff[0], drop_ff[1], out=h)       # in place: the saved h is the dropped one (dW2 needs that)
     x2 = torch.empty((N, dim), device=dev, dtype=at)
-    rowsq2 = torch.zeros(N, device=dev, dtype=torch.float32)
+    rowsq2 = _zeros(pool, N, dev)
     ops.gemm_(h, p["w2_c"], out=x2, bias=p["b2"], res=x1, row_sumsq=rowsq2, act_dtype=at)
     c = EncoderCtx()
     c.x, c.rowsq_x, c.s_a, c.qkv, c.o, c.lse = x2d, rowsq_x, s_a, qkv, o, lse
@@ -74,9 +101,17 @@ def encoder_fwd(x, rowsq_x, B, S, dim, p, heads, d, keep=True, drop_p=0.0, tag="
     return c
 
 
-def encoder_bwd(c: EncoderCtx, dx2, p, G, heads, d):
+def _skinny_split(N, d, K):
+    """do = dx1 @ Wo has a [N, d] output: with few 128-row tiles and a deep K (time axis: 66 tiles, K = 16 512) the
+    machine is half empty.  Those launches accumulate split-K partial sums into a zeroed f32 buffer (the launcher's
+    split heuristic) and one small cast produces the bf16 result."""
+    tiles = ((N + 127) // 128) * ((d + 127) // 128)
+    return tiles < 100 and K >= 4096
+
+
+def encoder_bwd(c: EncoderCtx, dx2, p, G, heads, d, tag=None, pool=None):
     """dx2: grad wrt the un-normalised encoder output x2 [N,dim] (act dtype).  G: dict key -> f32 grad sink tensor
-    (accumulated).  Returns grad wrt the encoder input x [N,dim]."""
+    (accumulated).  Returns grad wrt the encoder input x [N,dim].  tag: encoder name for the gradient-ready hooks."""
     N, dim = c.x.shape
     dev, at = dx2.device, dx2.dtype
     F = p["w1"].shape[0]
@@ -86,7 +121,9 @@ def encoder_bwd(c: EncoderCtx, dx2, p, G, heads, d):
         ops.colsum(dx2, G["b2"], accumulate=True)
     if "w2" in G:
         ops.gemm_(dx2, c.h, a_mn=True, b_mn=True, out=G["w2"], accumulate=True)                 # dW2 += dx2^T h
-    rowdot_f = torch.zeros(N, device=dev, dtype=torch.float32)
+    if tag:
+        _notify(tag, ("w2", "b2", "g_final"))
+    rowdot_f = _zeros(pool, N, dev)
     dfs = torch.empty((N, F), device=dev, dtype=at)      # s_f * dpre
     df = torch.empty((N, F), device=dev, dtype=at)       # dpre
     ops.gemm_(dx2, p["w2_c"], b_mn=True, out=dfs, out2=df, act=ops.ACT_GELU_BWD, aux=c.fpre, aux_bias=p["b1"],
@@ -103,13 +140,20 @@ def encoder_bwd(c: EncoderCtx, dx2, p, G, heads, d):
         ops.gemm_(dfs, c.x1, a_mn=True, b_mn=True, out=G["w1"], accumulate=True)               # dW1 += (s_f dpre)^T x1
     if "g_ff" in G:
         _acc_g(G["g_ff"], rowdot_f, p["g_ff"])
+    if tag:
+        _notify(tag, ("g_ff", "w1", "b1"))
     dx1 = torch.empty((N, dim), device=dev, dtype=at)
     ops.gemm_(dfs, p["w1_c"], b_mn=True, out=dx1, res=dx2, cx=c.x1, coef_num=rowdot_f, coef_den=c.rowsq1, act_dtype=at)
     # ---- attention ----------------------------------------------------------------------------------------------
     if "wo" in G:
         ops.gemm_(dx1, c.o.view(N, d), a_mn=True, b_mn=True, out=G["wo"], accumulate=True)     # dWo += dx1^T o
-    do = torch.empty((N, d), device=dev, dtype=at)
-    ops.gemm_(dx1, p["wo_c"], b_mn=True, out=do, act_dtype=at)                                 # do = dx1 Wo
+    if at == torch.bfloat16 and _skinny_split(N, d, dim):
+        do32 = _zeros(pool, N * d, dev).view(N, d)
+        ops.gemm_(dx1, p["wo_c"], b_mn=True, out=do32, accumulate=True)                        # do = dx1 Wo (split-K, f32)
+        do = ops.cast(do32, at)
+    else:
+        do = torch.empty((N, d), device=dev, dtype=at)
+        ops.gemm_(dx1, p["wo_c"], b_mn=True, out=do, act_dtype=at)                             # do = dx1 Wo
     dqkv = torch.empty((N, 3 * d), device=dev, dtype=at)
     q3, g3 = c.qkv.view(B, S, 3 * d), dqkv.view(B, S, 3 * d)
     ops.attn_bwd(q3[:, :, :d], q3[:, :, d:2 * d], q3[:, :, 2 * d:], c.o, do.view(B, S, d), c.lse, heads,
@@ -119,6 +163,8 @@ def encoder_bwd(c: EncoderCtx, dx2, p, G, heads, d):
         _acc_g(G["g_attn"], rowdot_a, p["g_attn"])
     if "wqkv" in G:
         ops.gemm_(dqkv, c.x, a_mn=True, b_mn=True, out=G["wqkv"], accumulate=True)             # dWqkv += (s_a dqkv)^T x
+    if tag:
+        _notify(tag, ("g_attn", "wqkv", "wo"))
     dx = torch.empty((N, dim), device=dev, dtype=at)
     ops.gemm_(dqkv, p["wqkv_c"], b_mn=True, out=dx, res=dx1, cx=c.x, coef_num=rowdot_a, coef_den=c.rowsq_x, act_dtype=at)
     return dx
@@ -150,17 +196,20 @@ class DuettEncodeFn(torch.autograd.Function):
                                                 tab.detach().contiguous(), at, training, return_hidden=True)
         encs = []
         src, src_rowsq, g_prev = psi0, None, None
+        pool = ZeroPool(2 * L * (B * V1 + B * T1) + 64, xs_feats.device)
         for l in range(L):
-            pe = _enc_params(det, f"event_transformers.{l}", at)
+            pe = _enc_params(det, f"event_transformers.{l}", at, P)
             x_e, rsq = ops.relayout_fwd(src, B, T1, V1, cfgd, src_rowsq=src_rowsq, g=g_prev,
                                         pos_bcast=det["full_event_embedding.weight"])
             dp = float(spec.get("dropout", 0.0)) if training else 0.0
-            ce = encoder_fwd(x_e.view(B, V1, E), rsq, B, V1, E, pe, heads, cfgd, drop_p=dp, tag=f"event_transformers.{l}")
-            pt = _enc_params(det, f"time_transformers.{l}", at)
+            ce = encoder_fwd(x_e.view(B, V1, E), rsq, B, V1, E, pe, heads, cfgd, drop_p=dp, tag=f"event_transformers.{l}",
+                             pool=pool)
+            pt = _enc_params(det, f"time_transformers.{l}", at, P)
             x_t, rsq = ops.relayout_fwd(ce.x2.view(B, V1, T1, cfgd), B, V1, T1, cfgd,
                                         src_rowsq=ce.rowsq2 if spec["final_norm"] else None, g=pe["g_final"],
                                         pos_batched=te.detach())
-            ct = encoder_fwd(x_t.view(B, T1, Ep), rsq, B, T1, Ep, pt, heads, cfgd, drop_p=dp, tag=f"time_transformers.{l}")
+            ct = encoder_fwd(x_t.view(B, T1, Ep), rsq, B, T1, Ep, pt, heads, cfgd, drop_p=dp, tag=f"time_transformers.{l}",
+                             pool=pool)
             encs.append((ce, ct))
             src, src_rowsq, g_prev = ct.x2.view(B, T1, V1, cfgd), (ct.rowsq2 if spec["final_norm"] else None), pt["g_final"]
         out, _ = ops.relayout_fwd(src.view(B * T1, 1, 1, Ep), B * T1, 1, 1, Ep, src_rowsq=src_rowsq, g=g_prev,
@@ -196,25 +245,24 @@ class DuettEncodeFn(torch.autograd.Function):
                                src_rowsq=ct.rowsq2 if fn else None, g=det[gname] if fn else None,
                                dg=sinks.get(gname) if fn else None).view(B * T1, Ep)
         dx_ts = []     # time-encoder input gradients of every layer: their sum is the time-embedding gradient
+        pool = ZeroPool(L * (B * V1 + B * T1) * (1 + cfgd) + 64, dev)       # row dots + split-K `do` partial sums
         for l in reversed(range(L)):
             ce, ct = encs[l]
             pt = _enc_params(det, f"time_transformers.{l}", at)
-            dx_t = encoder_bwd(ct, dx2, pt, _enc_sinks(sinks, f"time_transformers.{l}"), heads, cfgd)   # [B*T1, Ep]
+            dx_t = encoder_bwd(ct, dx2, pt, _enc_sinks(sinks, f"time_transformers.{l}"), heads, cfgd,
+                               tag=f"time_transformers.{l}", pool=pool)                                 # [B*T1, Ep]
             if ctx.te_requires_grad:
                 dx_ts.append(dx_t)
-            if GRAD_READY_HOOK is not None:
-                GRAD_READY_HOOK(f"time_transformers.{l}")
             # time-major grad -> event-major grad of the event encoder's un-normalised output (+ its final norm)
             gname = f"event_transformers.{l}.g_final"
             dx2e = ops.relayout_bwd(dx_t.view(B, T1, V1, cfgd), B, V1, T1, cfgd, src=ce.x2 if fn else None,
                                     src_rowsq=ce.rowsq2 if fn else None, g=det[gname] if fn else None,
                                     dg=sinks.get(gname) if fn else None).view(B * V1, E)
             pe = _enc_params(det, f"event_transformers.{l}", at)
-            dx_e = encoder_bwd(ce, dx2e, pe, _enc_sinks(sinks, f"event_transformers.{l}"), heads, cfgd)  # [B*V1, E]
+            dx_e = encoder_bwd(ce, dx2e, pe, _enc_sinks(sinks, f"event_transformers.{l}"), heads, cfgd,
+                               tag=f"event_transformers.{l}", pool=pool)                                # [B*V1, E]
             if "full_event_embedding.weight" in sinks:
                 ops.colsum(dx_e.view(B, V1 * E), sinks["full_event_embedding.weight"].view(-1), accumulate=True)
-            if GRAD_READY_HOOK is not None:
-                GRAD_READY_HOOK(f"event_transformers.{l}")
             if l > 0:
                 pce, pct = encs[l - 1]
                 gname = f"time_transformers.{l - 1}.g_final"
@@ -244,12 +292,20 @@ class DuettEncodeFn(torch.autograd.Function):
         return (None, None, dtab if ctx.tab_requires_grad else None, dte) + grads
 
 
-def _enc_params(det, prefix, at):
+def _enc_params(det, prefix, at, P=None):
+    """Encoder parameters + their act-dtype copies ('wqkv_c', ...).  bf16 mode: a parameter living in ddp.FlatParams with
+    bf16 shadows enabled hands out its shadow view (refreshed by the optimizer kernel) instead of being cast here."""
     p = {k: det[f"{prefix}.{k}"] for k in ENC_KEYS}
     for k in ("wqkv", "wo", "w1", "w2"):
         ck = f"{prefix}.{k}@{at}"
         if ck not in det:
-            det[ck] = ops.cast(p[k], at)
+            sh = None
+            if P is not None and at == torch.bfloat16:
+                src = P[f"{prefix}.{k}"]
+                sh = getattr(src, "_dx_shadow", None)
+                if sh is not None and getattr(src, "_dx_shadow_version", -1) != src._version:
+                    sh = None
+            det[ck] = sh if sh is not None else ops.cast(p[k], at)
         p[k + "_c"] = det[ck]
     return p
 

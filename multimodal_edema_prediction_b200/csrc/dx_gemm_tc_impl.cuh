@@ -223,6 +223,9 @@ struct TcParams {
   int splits, kb_per_split;              // split-K (dW GEMMs with few output tiles): partial sums are red.add'ed into out
   int epi_mask;                          // staged epilogue: compile-time feature mask (dx_epi_mask), -1 = runtime flags
   int raster_m;                          // 1: consecutive work units walk M first (few M tiles sharing a large B column block)
+  int fault;                             // test hook (DX_GEMM_FAULT): bit 0 = from a CTA's third tile on the accumulator is NOT reset, i.e. a
+                                         // TMEM slot-reuse bug (tests/test_gemm_production_gpu.py proves its checks catch it); bits 1 / 2 =
+                                         // the staged epilogue skips its side-tensor loads / its stores (timing experiments, wrong results)
 };
 
 // work unit -> tile indices.  The fast-running index is the one whose tiles share the LARGER operand block, so that block
@@ -298,6 +301,27 @@ __device__ __forceinline__ void lds8(uint32_t addr, float (&v)[8]) {
     v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
+__device__ __forceinline__ void lds_raw(uint32_t addr, uint4& u) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ void sts_raw(uint32_t addr, const uint4& u) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
 __device__ __forceinline__ void sts8(uint32_t addr, const float (&v)[8]) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -326,7 +350,8 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
   const bool has_x = CT ? ((MASK & (DX_M_CX | DX_M_GELUBWD)) != 0) : (e0.aux != nullptr || e0.cx != nullptr);
   const bool has_o2 = CT ? ((MASK & (DX_M_GELU | DX_M_GELUBWD)) != 0) : dx_epi_has_out2(e0);
   constexpr bool has_b = CT && ((MASK & (DX_M_BIAS | DX_M_GELUBWD)) != 0);   // bias (or aux_bias) staged in wbias
-  const bool any_in = has_res || has_x;
+  const bool xp_noload = (p.fault & 2) != 0, xp_nostore = (p.fault & 4) != 0;   // timing experiments only (DX_GEMM_FAULT bits)
+  const bool any_in = (has_res || has_x) && !xp_noload;
   const int ring = p.stage_ring;
   const bool pf_side = any_in && ring == 2;
   const uint32_t stg = smem_u32(wstg), sbias = smem_u32(wbias);
@@ -448,34 +473,64 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
       tmem_ld_wait();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        float v[32];
+        if constexpr (CT) {
+          // Three phases per 32-column half so that the shared-memory latencies overlap instead of chaining piece by piece
+          // (a load of piece j+1 cannot be hoisted above the store of piece j by ptxas: possible aliasing): (1) all side /
+          // bias loads of the 4 pieces, (2) arithmetic in registers, (3) all stores.
+          uint4 ur[4], ux[4];
+          float bv[4][8];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(vr[half][k]);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t px = (uint32_t)(half * 4 + j) << 4;
+            if (has_res) lds_raw(rowR ^ px, ur[j]);
+            if (has_x) lds_raw(rowX ^ px, ux[j]);
+            if (has_b) lds_f8(biasS + (half * 4 + j) * 32, bv[j]);
+          }
+          uint4 po[4], po2[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int piece = half * 4 + j;
-          const uint32_t px = (uint32_t)piece << 4;
-          const int ncol = nc + piece * 8;
-          float t[8], r[8], a[8], o2[8], bv[8];
+          for (int j = 0; j < 4; ++j) {
+            float t[8], r[8], a[8], o2[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
-          if (has_res) lds8(rowR ^ px, r);
-          if (has_x) lds8(rowX ^ px, a);
-          if (has_b) lds_f8(biasS + piece * 32, bv);
-          if constexpr (CT) {
+            for (int k = 0; k < 8; ++k) t[k] = __uint_as_float(vr[half][j * 8 + k]);
+            if (has_res) unpack8(ur[j], r);
+            if (has_x) unpack8(ux[j], a);
             // no bounds branch: out-of-range rows / columns hold zeros everywhere (operands, side blocks and bias are
             // zero-filled by TMA / cp.async), contribute nothing to the row sums, and are never stored or flushed
-            dx_epilogue_math_c<MASK>(rc, t, r, a, bv, o2, rs, rd);
-          } else if (row_ok && ncol < e.N) {   // N % 8 == 0 on this path: pieces are whole
-            dx_epilogue_math<8>(e, rc, ncol, 8, t, r, a, a, o2, rs, rd);   // aux and cx are mutually exclusive: `a` is both
+            dx_epilogue_math_c<MASK>(rc, t, r, a, bv[j], o2, rs, rd);
+            po[j] = pack8(t);
+            if (has_o2) po2[j] = pack8(o2);
           }
-          sts8(rowR ^ px, t);
-          if (has_o2) sts8(rowO ^ px, o2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t px = (uint32_t)(half * 4 + j) << 4;
+            sts_raw(rowR ^ px, po[j]);
+            if (has_o2) sts_raw(rowO ^ px, po2[j]);
+          }
+        } else {
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(vr[half][k]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int piece = half * 4 + j;
+            const uint32_t px = (uint32_t)piece << 4;
+            const int ncol = nc + piece * 8;
+            float t[8], r[8], a[8], o2[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = v[j * 8 + k];
+            if (has_res) lds8(rowR ^ px, r);
+            if (has_x) lds8(rowX ^ px, a);
+            if (row_ok && ncol < e.N) {   // N % 8 == 0 on this path: pieces are whole
+              dx_epilogue_math<8>(e, rc, ncol, 8, t, r, a, a, o2, rs, rd);   // aux and cx are mutually exclusive: `a` is both
+            }
+            sts8(rowR ^ px, t);
+            if (has_o2) sts8(rowO ^ px, o2);
+          }
         }
       }
       __syncwarp();
-      if (e.out) stage_store(bufR, e.out, e.ldo, m_base, nc, e.M, e.N, lane);
-      if (has_o2) stage_store(bufO, e.out2, e.ldo2, m_base, nc, e.M, e.N, lane);
+      if (e.out && !xp_nostore) stage_store(bufR, e.out, e.ldo, m_base, nc, e.M, e.N, lane);
+      if (has_o2 && !xp_nostore) stage_store(bufO, e.out2, e.ldo2, m_base, nc, e.M, e.N, lane);
       if (any_in) fence_proxy_async();   // generic-proxy accesses of these blocks are ordered before the next TMA write into them
       __syncwarp();
       side_loaded = next && pf_side;
@@ -670,8 +725,9 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
             // MN-major: advance 16 k-rows = two 1024 B swizzle atoms.
             const uint64_t ad = make_smem_desc(sa + (A_MN ? k * 2048 : k * 32), p.a_lbo, p.a_sbo);
             const uint64_t bd = make_smem_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
-            if (PAIR) umma_f16_pair(acc, ad, bd, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
-            else umma_f16(acc, ad, bd, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+            const uint32_t accf = (kb > kb_lo || k > 0 || ((p.fault & 1) && tcount >= 2)) ? 1u : 0u;
+            if (PAIR) umma_f16_pair(acc, ad, bd, idesc, accf);
+            else umma_f16(acc, ad, bd, idesc, accf);
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
           if (PAIR) umma_commit_pair(empty_bar + s);
@@ -793,6 +849,8 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   pp.tiles_m = dx_ceil_div(d->M, BM * CL);
   pp.raster_m = pp.tiles_m < pp.tiles_n ? 1 : 0;
   if (const char* env = getenv("DX_GEMM_RASTER_M")) pp.raster_m = atoi(env) != 0;
+  pp.fault = 0;
+  if (const char* env = getenv("DX_GEMM_FAULT")) pp.fault = atoi(env);   // bit 0: injected bug; bits 1, 2: skip the side loads / the stores
   long long total = (long long)pp.tiles_n * pp.tiles_m * (d->batch > 1 ? d->batch : 1);
   static int num_sms = 0;
   if (!num_sms) {

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(NT) adamw_kernel(float* __restrict__ p, const 
                                                   float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                   float wd, float bc1, float bc2, const float* __restrict__ gscale_ptr,
                                                   float gscale, const int* __restrict__ step_dev,
-                                                  const float* __restrict__ lr_scale_dev) {
+                                                  const float* __restrict__ lr_scale_dev, bf16* __restrict__ shadow) {
   const float gs = gscale_ptr ? gscale_ptr[0] * gscale : gscale;
   if (step_dev) {   // CUDA-graph friendly: the step counter (hence the bias correction) lives on the device
     const float st = (float)step_dev[0];
@@ -106,6 +106,13 @@ __global__ void __launch_bounds__(NT) adamw_kernel(float* __restrict__ p, const 
     reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
     reinterpret_cast<float4*>(m)[i] = make_float4(me[0], me[1], me[2], me[3]);
     reinterpret_cast<float4*>(v)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
+    if (shadow) {   // bf16 mirror of the updated weights (the tcgen05 GEMMs' operands): 2 B/param here instead of a cast pass
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pe[0], pe[1]), hi = __floats2bfloat162_rn(pe[2], pe[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(shadow)[i] = u;
+    }
   }
   for (long long i = (n4 << 2) + (long long)blockIdx.x * NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
     const float gi = g[i] * gs;
@@ -117,6 +124,7 @@ __global__ void __launch_bounds__(NT) adamw_kernel(float* __restrict__ p, const 
     v[i] = vi;
     const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
     p[i] = pi - (lr / bc1) * mi / denom;
+    if (shadow) shadow[i] = __float2bfloat16_rn(p[i]);
   }
 }
 
@@ -347,11 +355,13 @@ int dx_fusion_logits_bwd(const float* d_img, const float* d_ts, const float* d_s
 /* AdamW step on flat f32 buffers. Effective gradient = g * grad_scale * (grad_scale_dev ? *grad_scale_dev : 1). */
 int dx_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
              float weight_decay, int step, const float* grad_scale_dev, float grad_scale, const int* step_dev,
-             const float* lr_scale_dev, void* stream) {
+             const float* lr_scale_dev, void* shadow_bf16, void* stream) {
   DX_CHECK_ARG(p && g && m && v && n > 0 && (step >= 1 || step_dev), "dx_adamw: bad arguments");
+  DX_CHECK_ARG(!shadow_bf16 || ((uintptr_t)shadow_bf16 % 8 == 0) || ((uintptr_t)p % 16 != 0), "dx_adamw: shadow must be 8 B aligned");
   const float bc1 = 1.f - powf(beta1, (float)(step >= 1 ? step : 1)), bc2 = 1.f - powf(beta2, (float)(step >= 1 ? step : 1));
   adamw_kernel<<<grid_for(n), NT, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
-                                                             grad_scale_dev, grad_scale, step_dev, lr_scale_dev);
+                                                             grad_scale_dev, grad_scale, step_dev, lr_scale_dev,
+                                                             reinterpret_cast<bf16*>(shadow_bf16));
   DX_LAUNCH_CHECK();
   return DX_OK;
 }

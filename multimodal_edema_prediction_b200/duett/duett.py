@@ -260,6 +260,18 @@ class Model(nn.Module):
         state_dict = checkpoint["state_dict"]
         model_state_dict = self.state_dict()
         is_changed = False
+        # The tolerant logic below backfills missing keys and drops unknown ones.  For the axis encoders that would turn a
+        # key-layout mismatch into SILENTLY re-initialised transformers: the keys inside {event,time}_transformers.{l} belong
+        # to x_transformers, which the reference does not pin (state_keys.ENC_MAP / QKV hold the 1.x/2.x layout).  Refuse.
+        import re
+        enc = re.compile(r"^(event|time)_transformers\.\d+\.")
+        missing = sorted(k for k in model_state_dict if enc.match(k) and k not in state_dict)
+        unknown = sorted(k for k in state_dict if enc.match(k) and k not in model_state_dict)
+        if missing or unknown:
+            raise RuntimeError(
+                "checkpoint and model disagree on the x_transformers key layout of the axis encoders; loading would leave "
+                f"transformer weights randomly initialised.\n  expected but absent ({len(missing)}): {missing[:8]}\n  present but "
+                f"unmapped ({len(unknown)}): {unknown[:8]}\nAdd the checkpoint's layout to state_keys.ENC_MAP / state_keys.QKV.")
         for k in model_state_dict:
             if k not in state_dict:
                 state_dict[k] = model_state_dict[k]
@@ -312,6 +324,11 @@ class Model(nn.Module):
     def feats_to_input(self, x, batch_size, limits=None):
         xs_ts, xs_static, times = x
         xs_ts, times = list(xs_ts), list(times)
+        if len(xs_ts) and not torch.is_tensor(xs_ts[0]) and hasattr(xs_ts[0], "slot"):
+            # raw event rows from MIMICDataset.__getitem__ (host-only, DataLoader-worker safe): one dx_bin_events launch bins
+            # the whole batch on the device (duett/mimic_dataset.py:33-46 semantics), here in the main process
+            from .mimic_dataset import bin_stay_rows
+            xs_ts = list(bin_stay_rows(xs_ts, self.device).unbind(0))
         augment = self.training and (self.aug_noise > 0 or self.aug_mask > 0) and not self.pretrain
         if not augment and all(f.shape[0] <= self.max_len for f in xs_ts):
             # plain batch (evaluation, SSL, KD student): no per-sample work on the host - the samples are stacked into
@@ -359,6 +376,8 @@ class Model(nn.Module):
         there (engine._move_lists moves them sample by sample like the reference does)."""
         t0 = tensors[0]
         if t0.is_cuda or dev.type != "cuda":
+            if any(t.is_cuda != t0.is_cuda for t in tensors):          # device-binned x_ts next to host static / times
+                tensors = [t.to(dev, non_blocking=True) for t in tensors]
             return torch.stack(tensors).to(dev, non_blocking=True)
         shape = (len(tensors),) + tuple(t0.shape)
         st = self.__dict__.setdefault("_staging", {})

@@ -233,8 +233,9 @@ def dropout(x, p, training, tag="dropout"):
 # ---- losses (each returns scalars; gradients w.r.t. logits come from the same kernel launch) ----------------------------
 class KDLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z_s, z_t, y, T, alpha, pos_weight):
-        out, dz = ops.kd_loss(z_s.contiguous().float(), z_t.contiguous().float(), y.contiguous().float(), T, alpha, pos_weight)
+    def forward(ctx, z_s, z_t, y, T, alpha, pos_weight, eps=1e-7):
+        out, dz = ops.kd_loss(z_s.contiguous().float(), z_t.contiguous().float(), y.contiguous().float(), T, alpha, pos_weight,
+                              eps=eps)
         ctx.save_for_backward(dz)
         total, bce, kd = out[0], out[1], out[2]
         ctx.mark_non_differentiable(bce, kd)
@@ -243,7 +244,7 @@ class KDLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_total, g_bce, g_kd):
         (dz,) = ctx.saved_tensors
-        return ops.scale_dev(dz, g_total), None, None, None, None, None
+        return ops.scale_dev(dz, g_total), None, None, None, None, None, None
 
 
 class BCELogitsFn(torch.autograd.Function):

@@ -18,7 +18,7 @@ class VanillaKLKD(nn.Module):
         self.eps = eps
 
     def forward(self, z_s: torch.Tensor, z_t: torch.Tensor) -> torch.Tensor:
-        total, _, _ = KDLossFn.apply(z_s, z_t.detach(), torch.zeros_like(z_s, dtype=torch.float32), self.T, 0.0, None)
+        total, _, _ = KDLossFn.apply(z_s, z_t.detach(), torch.zeros_like(z_s, dtype=torch.float32), self.T, 0.0, None, self.eps)
         return total
 
 
@@ -47,7 +47,8 @@ class StudentKDLoss(nn.Module):
 
     def forward(self, z_s: torch.Tensor, z_t: torch.Tensor, y: torch.Tensor) -> dict:
         if isinstance(self.kd, VanillaKLKD):
-            total, bce, kd = KDLossFn.apply(z_s, z_t.detach(), y.float(), self.kd.T, self.alpha, self.pos_weight_value)
+            total, bce, kd = KDLossFn.apply(z_s, z_t.detach(), y.float(), self.kd.T, self.alpha, self.pos_weight_value,
+                                            self.kd.eps)
             return {"total": total, "bce": bce.detach(), "kd": kd.detach()}
         loss_kd = self.kd(z_s, z_t)
         pw = 1.0 if self.pos_weight_value is None else self.pos_weight_value

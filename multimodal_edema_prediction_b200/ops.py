@@ -133,6 +133,14 @@ def cast(x, dtype):
     return y
 
 
+def cast_into(x, y):
+    """y[:] = x converted to y's dtype (same numel)."""
+    _chk(x); _chk(y)
+    assert x.numel() == y.numel()
+    _call("dx_cast", _p(x), _dt(x), _p(y), _dt(y), x.numel())
+    return y
+
+
 def scalenorm_scale(rowsq, g, dim):
     out = torch.empty_like(rowsq)
     _call("dx_scalenorm_scale", _p(rowsq), _p(g), float(dim) ** 0.5, _p(out), rowsq.numel())
@@ -166,7 +174,11 @@ DROP_LOG = None      # tests set this to a list: every site appends (tag, p, see
 
 def drop_seed(tag="", p=0.0, shape=None):
     if _DROP["base"] is None:
-        _DROP["base"] = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019) & 0xFFFFFFFFFFFFFFFF
+        rank = 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank = torch.distributed.get_rank()      # data-parallel replicas draw different masks (each sees its own shard)
+        _DROP["base"] = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019
+                         + rank * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
     _DROP["site"] += 1
     seed = (_DROP["base"] + _DROP["site"] * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
     if DROP_LOG is not None:
@@ -375,13 +387,13 @@ def scatter_vec(src, offsets, dst, accumulate=True):
 
 
 # ---- losses --------------------------------------------------------------------------------------------------------------
-def kd_loss(zs, zt, y, T, alpha, pos_weight, need_grad=True):
+def kd_loss(zs, zt, y, T, alpha, pos_weight, need_grad=True, eps=1e-7):
     for t in (zs, zt, y):
         _chk(t, torch.float32)
     out = torch.empty(3, device=zs.device, dtype=torch.float32)
     dz = torch.empty_like(zs) if need_grad else None
     _call("dx_kd_loss", _p(zs), _p(zt), _p(y), zs.numel(), float(T), float(alpha),
-          -1.0 if pos_weight is None else float(pos_weight), 1e-7, _p(out), _p(dz))
+          -1.0 if pos_weight is None else float(pos_weight), float(eps), _p(out), _p(dz))
     return out, dz
 
 
@@ -476,11 +488,14 @@ def fusion_logits_bwd(d_img, d_ts, d_scaled, d_fus, corr, beta, dbeta, dbias_i, 
 
 # ---- optimizer -------------------------------------------------------------------------------------------------------------
 def adamw(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale_dev=None, grad_scale=1.0, step_dev=None,
-          lr_scale_dev=None):
+          lr_scale_dev=None, shadow=None):
     for t in (p, g, m, v):
         _chk(t, torch.float32)
+    if shadow is not None:
+        _chk(shadow, torch.bfloat16)
+        assert shadow.numel() == p.numel()
     _call("dx_adamw", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
-          float(weight_decay), int(step), _p(grad_scale_dev), float(grad_scale), _p(step_dev), _p(lr_scale_dev))
+          float(weight_decay), int(step), _p(grad_scale_dev), float(grad_scale), _p(step_dev), _p(lr_scale_dev), _p(shadow))
 
 
 def sumsq(x, out):

@@ -343,10 +343,10 @@ def _with_grad(fn, z, *args):
     return out, dz
 
 
-def kd_loss(zs, zt, y, T, alpha, pos_weight, need_grad=True):
+def kd_loss(zs, zt, y, T, alpha, pos_weight, need_grad=True, eps=1e-7):
     def fn(z):
-        pt = torch.sigmoid(zt / T).clamp(1e-7, 1 - 1e-7)
-        ps = torch.sigmoid(z / T).clamp(1e-7, 1 - 1e-7)
+        pt = torch.sigmoid(zt / T).clamp(eps, 1 - eps)
+        ps = torch.sigmoid(z / T).clamp(eps, 1 - eps)
         kd = T * T * (pt * (pt.log() - ps.log()) + (1 - pt) * ((1 - pt).log() - (1 - ps).log())).mean()
         pw = None if pos_weight is None else torch.tensor([pos_weight])
         bce = F.binary_cross_entropy_with_logits(z, y, pos_weight=pw)
@@ -443,7 +443,7 @@ def fusion_logits_bwd(d_img, d_ts, d_scaled, d_fus, corr, beta, dbeta, dbias_i, 
 
 
 def adamw(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale_dev=None, grad_scale=1.0, step_dev=None,
-          lr_scale_dev=None):
+          lr_scale_dev=None, shadow=None):
     if step_dev is not None:
         step = int(step_dev[0])
     if lr_scale_dev is not None:
@@ -455,6 +455,13 @@ def adamw(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale_dev=None, g
     v.mul_(betas[1]).add_((1 - betas[1]) * gi * gi)
     bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
     p.sub_((lr / bc1) * m / (v.sqrt() / math.sqrt(bc2) + eps))
+    if shadow is not None:
+        shadow.copy_(p)
+
+
+def cast_into(x, y):
+    y.copy_(x)
+    return y
 
 
 def sumsq(x, out):
@@ -489,7 +496,7 @@ EMULATED = ["binary_auc", "sum_n", "dropout", "rowdot_bias", "gemm_", "relayout_
             "attn_fwd", "attn_bwd", "embed_fwd", "embed_bwd", "bn2d_fwd", "bn2d_bwd", "layernorm_fwd", "layernorm_bwd",
             "mean_rows", "mean_rows_bwd", "gather_vec", "scatter_vec", "kd_loss", "bce_logits", "masked_mse_bce",
             "masked_bce_cols", "aux_residual_kl", "require_device", "act_bwd", "act_fwd", "scale_dev", "sum_div_acc", "fusion_logits",
-            "fusion_logits_bwd", "adamw", "sumsq", "clip_factor"]
+            "fusion_logits_bwd", "adamw", "sumsq", "clip_factor", "cast_into"]
 
 
 def install(monkeypatch):

@@ -31,8 +31,10 @@ def _worker(rank, world, port, q):
         from multimodal_edema_prediction_b200.ddp import FlatParams, FusedAdamW, GradReducer
         from multimodal_edema_prediction_b200.loss.losses_duett import StudentKDLoss
         from multimodal_edema_prediction_b200.models.main_architecture_duett import DuettFeatureExtractor, StudentModel
-        torch.manual_seed(0)                                         # identical replicas
+        torch.manual_seed(100 + rank)                                # replicas start DIFFERENT (per-rank seed / checkpoint)
         student = StudentModel(DuettFeatureExtractor(pretrain=False, **KW), head_hidden=16, head_dropout=0.0).train()
+        with torch.no_grad():
+            student.duett.tab_encoder[3].batch_norm.running_mean.add_(float(rank))     # ... including BatchNorm buffers
         cfg = O.DuettConfig(3, 5, 4, d_embedding=8, n_layers=2, d_feedforward=96)
         b = O.synth_batch(cfg, 6, seed=100 + rank)                   # each rank its own shard
         z_t = torch.randn(6, generator=torch.Generator().manual_seed(rank))
@@ -42,19 +44,25 @@ def _worker(rank, world, port, q):
             z = student(b["x_ts"], b["x_static"], list(b["bin_ends"]))
             loss_fn(z, z_t, b["y"])["total"].backward()
 
-        # 1) plain autograd grads of this rank (no flat buffer yet)
-        local_step()
-        local = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p))   # SSL/supervised heads are unused here
-                 for n, p in student.named_parameters()}
-        # 2) flat-buffer + overlapped bucketed all-reduce
+        # 0) FlatParams broadcasts rank 0's parameters and buffers, like DDP does at construction
         flat = FlatParams(student)
+        for t in [flat.data] + [bf.float() for bf in student.buffers()]:
+            hi, lo = t.clone(), t.clone()
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            assert torch.equal(hi, lo), "replicas differ after FlatParams construction"
+        # 1) this rank's own gradients (no reducer attached: nothing is communicated)
+        flat.zero_grad()
+        local_step()
+        local = {n: p.grad.clone() for n, p in student.named_parameters()}
+        # 2) overlapped bucketed all-reduce
         red = GradReducer(flat).attach()
         opt = FusedAdamW(flat, lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
         opt.zero_grad()
         red.start_step()
         local_step()
         scale = red.finish()
-        assert scale == 0.5 and red.launched >= 4, red.launched     # one bucket per encoder (2 layers x 2 axes) + tail
+        assert scale == 0.5 and red.launched >= 12, red.launched    # 3 weight-group buckets per encoder (2 layers x 2 axes) + rest
         errs = []
         for n, p in student.named_parameters():
             parts = [torch.zeros_like(local[n]) for _ in range(world)]
@@ -63,9 +71,12 @@ def _worker(rank, world, port, q):
             errs.append(float((p.grad * scale - want).abs().max()))
         # 3) fused AdamW on the flat buffers == torch.optim.AdamW on the averaged grads with global-norm clipping
         ref_params = [torch.nn.Parameter(p.detach().clone()) for p in flat.params]
-        for rp, p in zip(ref_params, flat.params):
-            rp.grad = p.grad.detach().clone() * scale
-        torch.nn.utils.clip_grad_norm_(ref_params, 1.0)
+        assert any(n.startswith("duett.head.") for n in flat.unused) and any("pretrain_value_proj" in n for n in flat.unused)
+        for n, rp, p in zip(flat.names, ref_params, flat.params):
+            # parameters the student never uses (the backbone's own supervised / SSL heads) have .grad None under torch
+            # autograd: torch.optim.AdamW skips them (no weight decay either) and so must FusedAdamW
+            rp.grad = None if n in flat.unused else p.grad.detach().clone() * scale
+        torch.nn.utils.clip_grad_norm_([rp for rp in ref_params if rp.grad is not None], 1.0)
         ropt = torch.optim.AdamW(ref_params, lr=1e-3, weight_decay=0.01)
         ropt.step()
         opt.step(grad_scale=scale)
