@@ -335,7 +335,7 @@ class Workload:
                 p.requires_grad = False
             self.kd = StudentKDLoss().to(device)
         self.trainable = self.model
-        self.flat = FlatParams(self.trainable)
+        self.flat = FlatParams(self.trainable, broadcast=attach)
         if shadow and precision == "bf16":
             self.flat.enable_shadow()          # bf16 weight shadows refreshed by the optimizer kernel (no cast launches)
         if self.task == "ssl":                 # duett/duett.py:325-327 + train_duett_ssl.py:27-50,191
@@ -373,7 +373,7 @@ class Workload:
         return sum(t.numel() * t.element_size() for t in st.values())
 
     # ---- forward + loss on device-resident inputs ---------------------------------------------------------------
-    def loss_fn(self, st):
+    def loss_fn(self, st, z_t=None):
         if self.task == "supervised":
             y_hat = self.model.forward((st["xs_static"], st["xs_ts"], st["xs_times"], self.n_steps))
             return self.model._supervised_loss(y_hat, st["y"])
@@ -384,8 +384,10 @@ class Workload:
         # module API takes are views of the static tensors (feats_to_input re-appends the mask column on the device)
         x_ts = tuple(st["xs_ts"][:, :, :-1].unbind(0))
         x_static, bin_ends = tuple(st["xs_static"].unbind(0)), tuple(st["xs_times"].unbind(0))
-        with torch.no_grad():
-            z_t = self.teacher(x_ts, x_static, bin_ends, st["pix"])["main_logit"]
+        if z_t is None:
+            with torch.no_grad():
+                z_t = self.teacher(x_ts, x_static, bin_ends, st["pix"])["main_logit"]
+        self.last_z_t = z_t
         z_s = self.model(x_ts, x_static, bin_ends)
         return self.kd(z_s, z_t, st["y"])["total"]
 
@@ -414,6 +416,8 @@ def main():
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-out", default=None, help="write the per-shape GEMM timing table to this JSON file")
+    ap.add_argument("--comm-trace", default=None, help="N>1: also run traced eager steps and write the per-bucket all-reduce "
+                                                       "timeline (ready / start / end vs the backward) to this JSON file")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config], key=args.config)
     if args.impl == "reference":
@@ -455,7 +459,9 @@ def main():
             gstep = CudaGraphStep(lambda: wl.train_step(static), static, warmup=max(args.warmup, 3))
             launches_per_graph = (ops.launches() - l0) // (max(args.warmup, 3) + 1)
             # SURVEY §8(d) also asks for the step WITHOUT the optimizer (fwd + loss + bwd + all-reduce): a second graph
-            gstep_noopt = CudaGraphStep(lambda: wl.train_step(static, optimizer=False), static, warmup=3)
+            # (same memory pool: the two graphs are never replayed concurrently, and at the stress shape a second private
+            # pool of saved activations would not fit next to the eager profiling pass)
+            gstep_noopt = CudaGraphStep(lambda: wl.train_step(static, optimizer=False), static, warmup=3, pool=gstep.graph.pool())
         except Exception as ex:          # capture unsupported in this configuration: run eagerly and say so
             import traceback
             traceback.print_exc(file=sys.stderr)
@@ -553,12 +559,43 @@ def main():
         ms_noopt, _, _ = timed(step_noopt, args.steps)
     assert len(e2e_state["losses"]) == args.steps and all(l == l for l in e2e_state["losses"]), "e2e: a loss was not read back"
 
+    # ---- all-reduce overlap evidence: per-bucket events of a few traced eager steps ------------------------------------------
+    comm = None
+    if args.comm_trace and world > 1:
+        wl.red.trace = True
+        steps_tl = []
+        for i in range(4):
+            ev_b0, ev_b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            st_ = dev_batches[i % nb]
+            wl.opt.zero_grad()
+            wl.red.start_step()
+            loss_ = wl.loss_fn(st_)
+            ev_b0.record()
+            loss_.backward()
+            ev_b1.record()
+            scale_ = wl.red.finish()
+            ev_f = torch.cuda.Event(enable_timing=True)
+            ev_f.record()
+            wl.opt.step(grad_scale=scale_)
+            torch.cuda.synchronize()
+            t0 = wl.red._t0
+            steps_tl.append({"backward_start_ms": t0.elapsed_time(ev_b0), "backward_end_ms": t0.elapsed_time(ev_b1),
+                             "allreduce_all_done_ms": t0.elapsed_time(ev_f),
+                             "buckets": [{"MB": mb, "ready_ms": r, "start_ms": s_, "end_ms": e_} for mb, r, s_, e_ in wl.red.timeline()]})
+        wl.red.trace = False
+        last = steps_tl[-1]
+        exposed = last["allreduce_all_done_ms"] - last["backward_end_ms"]
+        comm = {"steps": steps_tl, "exposed_after_backward_ms": exposed, "n_buckets": len(last["buckets"]),
+                "total_MB": sum(b["MB"] for b in last["buckets"])}
+        if rank == 0:
+            os.makedirs(os.path.dirname(os.path.abspath(args.comm_trace)), exist_ok=True)
+            json.dump(comm, open(args.comm_trace, "w"), indent=1)
+        comm = {k: v for k, v in comm.items() if k != "steps"}
+
     # ---- parity of the measured configuration: graph-replayed bf16 step vs the eager fp32-mode step, same weights/batch ----
     parity = None
-    if not args.no_parity_check and rank == 0:
+    if not args.no_parity_check and world == 1:      # single-process check (it builds a replica and steps it without collectives)
         parity = parity_check(cfg, wl, gstep, dev_batches[0], device)
-    if world > 1:
-        barrier()
 
     if rank == 0:
         pk = peaks()
@@ -578,16 +615,27 @@ def main():
                          "tflops": v[1] / (v[3] * 1e-3) / 1e12, "gbs": v[2] / (v[3] * 1e-3) / 1e9,
                          "frac_of_speed_of_light": sol(v[1], v[2]) / (v[3] * 1e-3)}
                         for s, v in by_shape.items()), key=lambda r: -r["ms_per_step"])
+        # ---- the other half of the metric: the dual-axis attention kernels -----------------------------------------------
+        attn = {}
+        for (t, s_, f, b, a, z) in prof:
+            if t.startswith("attn"):
+                d = attn.setdefault((t, s_), [0, 0.0, 0.0, 0.0])
+                d[0] += 1; d[1] += f; d[2] += b; d[3] += a.elapsed_time(z)
+        attn_rec = {"kernels": [{"kind": k[0], "shape": k[1], "launches_per_step": v[0] / esteps, "us_per_launch": v[3] / v[0] * 1e3,
+                                 "tflops": v[1] / (v[3] * 1e-3) / 1e12, "gbs": v[2] / (v[3] * 1e-3) / 1e9} for k, v in sorted(attn.items())],
+                    "ms_per_step": sum(v[3] for v in attn.values()) / esteps,
+                    "share_of_step": sum(v[3] for v in attn.values()) / esteps / (ms_eager / esteps),
+                    "tensor_pipe_util_ncu": _attn_ncu()}
         if args.profile_out:
             os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
             ffma = {}
             for (t, s, f, b, a, z) in prof:
-                if t != "tc":
+                if t == "ffma":
                     d = ffma.setdefault(s, [0, 0.0])
                     d[0] += 1; d[1] += a.elapsed_time(z)
             json.dump({"config": cfg["key"], "per_gpu_batch": B, "ms_per_step": ms / args.steps, "eager_ms_per_step": ms_eager / esteps,
                        "gemm_ms_per_step": tot_ms / esteps, "gemm_share_of_step": (tot_ms / esteps) / (ms_eager / esteps),
-                       "by_shape": table, "ffma_by_shape": {k: {"launches_per_step": v[0] / esteps, "ms_per_step": v[1] / esteps} for k, v in ffma.items()}},
+                       "attn": attn_rec, "by_shape": table, "ffma_by_shape": {k: {"launches_per_step": v[0] / esteps, "ms_per_step": v[1] / esteps} for k, v in ffma.items()}},
                       open(args.profile_out, "w"), indent=1)
         # the family mixes tensor-bound (deep K) and HBM-bound (K <= 512, N = dim) launches: per-launch speed of light
         # max(flops / bf16 peak, algorithmic bytes / copy bandwidth), summed, against the measured time
@@ -631,13 +679,13 @@ def main():
                            l2="working set >> 126 MB L2 (every residual-stream tensor alone exceeds it), distinct input batches cycled"),
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": wl.h2d_bytes(dev_batches[0]), "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "cpu_baseline_c1": cpu_c1, "clocks": clk,
+            "gpu_launches": launches, "roofline": roof, "attn": attn_rec, "cpu_baseline": cpu, "cpu_baseline_c1": cpu_c1, "clocks": clk,
             "parity_check": parity,
             "model_tflops": value * fl / 1e12,
             "model_frac_of_bf16_peak": value * fl / 1e12 / (world * pk["bf16_tflops_sustained"]),
             "fwd_bwd_allreduce_only": None if ms_noopt is None else {
                 "value": world * B * args.steps / (ms_noopt / 1e3), "unit": "samples/s", "ms_per_step": ms_noopt / args.steps},
-            "allreduce_buckets_per_step": wl.red.launched, "host_enqueue_ms_per_step": host_ms,
+            "allreduce_buckets_per_step": wl.red.launched, "allreduce_trace": comm, "host_enqueue_ms_per_step": host_ms,
             "cuda_graph": gstep is not None, "cuda_graph_error": graph_err, "eager_ms_per_step": ms_eager / esteps,
         }
         if args.batch:
@@ -652,6 +700,14 @@ def main():
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def _attn_ncu():
+    """sm__pipe_tensor_cycles_active of the attention kernels from the committed ncu capture (profiles/), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_attn_tensor_pipe.json")))
+    except Exception:
+        return None
 
 
 def parity_check(cfg, wl, gstep, st, device):
@@ -686,12 +742,22 @@ def parity_check(cfg, wl, gstep, st, device):
         wl.flat.sync_shadow()
         loss16e = wl.train_step(st, optimizer=False)             # bf16, eager, no weight update
         torch.cuda.synchronize()
-        l16e, g16e = float(loss16e), float(wl.flat.grad.double().norm())
+        l16e, g16e = float(loss16e.detach()), float(wl.flat.grad.double().norm())
         wl32.opt.zero_grad()
-        loss32 = wl32.loss_fn(st)
+        # kd: the fp32 student is distilled from the SAME teacher logits as the bf16 one (the KD gradient is proportional to
+        # sigmoid(z_s/T) - sigmoid(z_t/T), a difference of nearly equal numbers at initialisation, so the bf16 rounding of the
+        # frozen teacher's logits would otherwise dominate the comparison of the student's gradients); the teacher's own
+        # bf16-vs-fp32 deviation is reported separately
+        zt16 = wl.last_z_t.detach().float() if wl.task == "kd" else None
+        loss32 = wl32.loss_fn(st, z_t=zt16)
         loss32.backward()
         torch.cuda.synchronize()
-        l32, g32 = float(loss32), float(wl32.flat.grad.double().norm())
+        l32, g32 = float(loss32.detach()), float(wl32.flat.grad.double().norm())
+        teacher_dev = None
+        if wl.task == "kd":
+            with torch.no_grad():
+                wl32.loss_fn(st)
+            teacher_dev = rel(zt16, wl32.last_z_t.float())
         # the graph replay on the same batch: its optimizer step runs after the loss and the gradients are complete
         wl.trainable.load_state_dict(sd)
         wl.flat.sync_shadow()
@@ -699,12 +765,13 @@ def parity_check(cfg, wl, gstep, st, device):
         if gstep is not None:
             loss16g = gstep(**st)
             torch.cuda.synchronize()
-            l16g, g16g = float(loss16g), float(wl.flat.grad.double().norm())
+            l16g, g16g = float(loss16g.detach()), float(wl.flat.grad.double().norm())
         r = lambda a, b: abs(a - b) / max(abs(b), 1e-30)
         loss_bound = 1e-1 if cfg["task"] == "supervised" else 2e-2
         res = {"tokens_rel_err_bf16_vs_fp32": tok_err, "loss_bf16_graph": l16g, "loss_bf16_eager": l16e, "loss_fp32_eager": l32,
                "loss_rel_err_graph_vs_eager": r(l16g, l16e), "loss_rel_err_bf16_vs_fp32": r(l16g, l32),
                "grad_norm_bf16_graph": g16g, "grad_norm_fp32_eager": g32, "grad_norm_rel_err": r(g16g, g32),
+               "teacher_logits_rel_err_bf16_vs_fp32": teacher_dev,
                "bounds": {"tokens": 2e-2, "graph_vs_eager": 2e-2, "loss_bf16_vs_fp32": loss_bound}}
         res["ok"] = bool(tok_err < 2e-2 and res["loss_rel_err_graph_vs_eager"] < 2e-2 and res["loss_rel_err_bf16_vs_fp32"] < loss_bound)
         del wl32

@@ -81,7 +81,9 @@ typedef struct dx_gemm_desc {
   int32_t rowvec_bs;                 /* stride of the [M] row vectors (row_scale, coef_num, row_sumsq, ...) between batches */
   int32_t split_k;                   /* FFMA kernel only: >1 splits K over blockIdx.z; needs accumulate into a zeroed f32 out,
                                         plain epilogue (bias allowed).  The tcgen05 kernel picks its own split for dW GEMMs. */
-  int32_t reserved;
+  int32_t allow_tf32;                /* fp32 operands: 1 = contract on the tensor cores (tcgen05 kind::tf32, fp32 accumulate) — the
+                                        precision of the reference's SSL / fine-tune path (set_float32_matmul_precision('high'),
+                                        duett/duett.py:9); 0 = exact fp32 FFMA products (the 1e-3 parity mode) */
 } dx_gemm_desc;
 
 int dx_gemm(const dx_gemm_desc* d, void* stream);
@@ -249,6 +251,15 @@ int dx_binary_auc(const float* logits, const float* labels, int64_t n, float* ke
  * float64 arithmetic, one rounding to float32: bit-identical to the reference. */
 int dx_bin_events(const int* slot, const double* vals, const double* cnts, const int64_t* row_start, const double* means,
                   const double* stds, int B, int T, int V, float* x, void* stream);
+
+/* ---- SSL masking ------------------------------------------------------------------------------------------
+ * Model.pretrain_prep_batch (duett/duett.py:189-237, pretrain_masked_steps == 1) as one launch.  The random draws stay on
+ * the host (numpy Generator, same order as the reference: per sample one timestep then one variable, then the [B,V]
+ * variable-dropout matrix) and arrive as index arrays: step [B] int32, ev [B] int32 (NULL = predict_events off),
+ * keep [B,V] uint8 (NULL = pretrain_dropout 0).  xs [B,T,2V+1] f32 -> xc (masked copy), y_ts / y_mask [B,V] (values and
+ * clipped counts of the masked timestep), y_ev / y_ev_mask [B,T] (the masked variable's column).  Bit-exact selection. */
+int dx_ssl_mask(const float* xs, const int* step, const int* ev, const unsigned char* keep, int B, int T, int V, float* xc,
+                float* y_ts, float* y_mask, float* y_ev, float* y_ev_mask, void* stream);
 
 #ifdef __cplusplus
 }

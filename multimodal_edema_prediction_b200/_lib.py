@@ -78,7 +78,7 @@ class GemmDesc(C.Structure):
         ("force_simt", C.c_int32), ("batch", C.c_int32),
         ("a_bs", C.c_int64), ("b_bs", C.c_int64), ("out_bs", C.c_int64), ("out2_bs", C.c_int64), ("res_bs", C.c_int64),
         ("aux_bs", C.c_int64), ("cx_bs", C.c_int64), ("bias_bs", C.c_int32), ("rowvec_bs", C.c_int32),
-        ("split_k", C.c_int32), ("reserved", C.c_int32),
+        ("split_k", C.c_int32), ("allow_tf32", C.c_int32),
     ]
 
 
@@ -101,7 +101,7 @@ def _ld(t: torch.Tensor) -> int:
 def make_gemm_desc(a: torch.Tensor, b: torch.Tensor, *, a_mn=False, b_mn=False, out=None, out2=None,
                    accumulate=False, act=ACT_NONE, act_dtype=None, row_scale=None, row_scale2=None, bias=None,
                    res=None, aux=None, aux_bias=None, cx=None, coef_num=None, coef_den=None, row_sumsq=None,
-                   row_dot=None, force_simt=False, split_k=0) -> GemmDesc:
+                   row_dot=None, force_simt=False, split_k=0, tf32=False) -> GemmDesc:
     """a: [M,K] (or [K,M] when a_mn), b: [N,K] (or [K,N] when b_mn); both 2-D with unit inner stride.
     Grouped mode: every matrix argument carries a leading batch dim ([G,M,K], [G,N,K], out [G,M,N], ...; arbitrary batch
     stride), bias is [G,N] and row vectors are [G,M]."""
@@ -154,6 +154,7 @@ def make_gemm_desc(a: torch.Tensor, b: torch.Tensor, *, a_mn=False, b_mn=False, 
             setattr(d, name, t.data_ptr())
     d.force_simt = int(force_simt)
     d.split_k = int(split_k)
+    d.allow_tf32 = int(bool(tf32))
     return d
 
 

@@ -182,6 +182,16 @@ class DuettEncodeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, xs_feats, tab, te, *params):
+        with ops.tf32_mode(spec.get("tf32", False)):
+            return DuettEncodeFn._forward(ctx, spec, xs_feats, tab, te, *params)
+
+    @staticmethod
+    def backward(ctx, gout):
+        with ops.tf32_mode(ctx.spec.get("tf32", False)):
+            return DuettEncodeFn._backward(ctx, gout)
+
+    @staticmethod
+    def _forward(ctx, spec, xs_feats, tab, te, *params):
         names = spec["names"]
         P = dict(zip(names, params))
         cfgd, V, T, L = spec["d"], spec["V"], spec["T"], spec["n_layers"]
@@ -221,7 +231,7 @@ class DuettEncodeFn(torch.autograd.Function):
         return out.view(B, T1, Ep)
 
     @staticmethod
-    def backward(ctx, gout):
+    def _backward(ctx, gout):
         spec, encs, P, B = ctx.spec, ctx.encs, ctx.P, ctx.B
         names = spec["names"]
         cfgd, V, T, L = spec["d"], spec["V"], spec["T"], spec["n_layers"]

@@ -46,6 +46,12 @@ int dx_gemm(const dx_gemm_desc* d, void* stream) {
   int rc = check_gemm(d);
   if (rc) return rc;
   if (d->in_dtype == DX_BF16 && !d->force_simt) return dx_gemm_tc_launch(d, 0, 0, -1, -1, -1, -1, (cudaStream_t)stream);
+  // fp32 operands: exact FFMA products by default; allow_tf32 opts into the tensor cores (kind::tf32: 10-bit mantissa
+  // products, fp32 accumulate — the reference's own SSL / fine-tune precision, torch.set_float32_matmul_precision('high'),
+  // duett/duett.py:9).  Layouts the TMA cannot address (row pitch not a multiple of 16 B, split_k) stay on FFMA.
+  if (d->in_dtype == DX_F32 && d->allow_tf32 && !d->force_simt && d->split_k <= 1 && (d->lda % 4 == 0) && (d->ldb % 4 == 0) &&
+      ((uintptr_t)d->A % 16 == 0) && ((uintptr_t)d->B % 16 == 0) && d->K >= 32 && (d->batch <= 1 || ((d->a_bs % 4 == 0) && (d->b_bs % 4 == 0))))
+    return dx_gemm_tc_launch(d, 0, 0, -1, -1, -1, -1, (cudaStream_t)stream);
   return dx_gemm_simt_launch(d, (cudaStream_t)stream);
 }
 

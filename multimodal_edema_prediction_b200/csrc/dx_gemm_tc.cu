@@ -3,6 +3,7 @@
 
 namespace dx_tc {
 DX_TC_ALL_GROUPS(DX_TC_DECLARE)
+DX_TC_GROUP_8(DX_TC32_DECLARE)
 }
 
 using namespace dx_tc;
@@ -30,12 +31,13 @@ int get_encode_fn() {
 // 3-D bf16 tensor map: dim0 = contiguous (size inner), dim1 = rows (size outer, stride ld elements),
 // dim2 = batch (stride bs elements).
 int make_tmap(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int batch, long long bs,
-              int box_inner, int box_outer) {
+              int box_inner, int box_outer, int esz = 2) {
   cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(batch > 1 ? batch : 1)};
-  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? bs * 2 : ld * 2)};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * esz, (cuuint64_t)(batch > 1 ? bs * esz : ld * esz)};
   cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = g_encode(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                        const_cast<void*>(base), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -86,6 +88,54 @@ int launch_major(const dx_gemm_desc* d, int bn, int stages, int ctas, const CUte
   return DX_ERR_UNSUPPORTED;
 }
 
+// fp32 operands on kind::tf32 (direct epilogue, single CTA)
+template <bool A_MN, bool B_MN>
+int launch_tf32_major(const dx_gemm_desc* d, int bn, int stages, const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& p,
+                      const DxEpi& e, cudaStream_t stream) {
+  if (bn == 256 && stages == 4) return launch_cfg<256, 4, A_MN, B_MN, false, 1, true>(d, ta, tb, ta, ta, p, e, stream);
+  if (bn == 192 && stages == 4) return launch_cfg<192, 4, A_MN, B_MN, false, 1, true>(d, ta, tb, ta, ta, p, e, stream);
+  if (bn == 128 && stages == 6) return launch_cfg<128, 6, A_MN, B_MN, false, 1, true>(d, ta, tb, ta, ta, p, e, stream);
+  if (bn == 64 && stages == 6) return launch_cfg<64, 6, A_MN, B_MN, false, 1, true>(d, ta, tb, ta, ta, p, e, stream);
+  dx_set_error("dx_gemm_tc: no tf32 instance for BN=%d stages=%d", bn, stages);
+  return DX_ERR_UNSUPPORTED;
+}
+
+int launch_tf32(const dx_gemm_desc* d, cudaStream_t stream) {
+  const int batch = d->batch > 1 ? d->batch : 1;
+  DX_CHECK_ARG(((uintptr_t)d->A % 16 == 0) && ((uintptr_t)d->B % 16 == 0), "dx_gemm_tc(tf32): A/B must be 16 B aligned");
+  DX_CHECK_ARG((d->lda % 4 == 0) && (d->ldb % 4 == 0), "dx_gemm_tc(tf32): lda/ldb must be multiples of 4 (got %lld, %lld)",
+               (long long)d->lda, (long long)d->ldb);
+  DX_CHECK_ARG(batch == 1 || ((d->a_bs % 4 == 0) && (d->b_bs % 4 == 0)), "dx_gemm_tc(tf32): batch strides must be multiples of 4");
+  DX_CHECK_ARG(batch <= 65535, "dx_gemm_tc: batch too large");
+  DxEpi e = dx_make_epi(d);
+  int bn = d->N <= 64 ? 64 : (d->N >= 256 ? 256 : 128);
+  if (d->N > 128 && d->N < 1024 && (d->N % 256) > 128 && (d->N % 256) <= 192 && (d->N % 192) == 0) bn = 192;
+  const int stages = bn >= 192 ? 4 : 6;
+  constexpr int BKE = 32, CHE = 32;    // fp32 elements per 128 B swizzle row
+  CUtensorMap ta, tb;
+  int rc;
+  if (!d->a_mn) rc = make_tmap(&ta, d->A, d->K, d->M, d->lda, batch, d->a_bs, BKE, BM, 4);
+  else rc = make_tmap(&ta, d->A, d->M, d->K, d->lda, batch, d->a_bs, CHE, BKE, 4);
+  if (rc) return rc;
+  if (!d->b_mn) rc = make_tmap(&tb, d->B, d->K, d->N, d->ldb, batch, d->b_bs, BKE, bn, 4);
+  else rc = make_tmap(&tb, d->B, d->N, d->K, d->ldb, batch, d->b_bs, CHE, BKE, 4);
+  if (rc) return rc;
+  TcParams p;
+  p.K = d->K;
+  // MN-major: LBO = distance between 32-element MN chunks (one {32 mn, 32 k} box = 4096 B), SBO = 8 k-rows (1024 B)
+  p.a_lbo = d->a_mn ? BKE * 128 : 16;
+  p.a_sbo = 1024;
+  p.b_lbo = d->b_mn ? BKE * 128 : 16;
+  p.b_sbo = 1024;
+  p.stage_bufs = 0;
+  p.stage_ring = 1;
+  p.epi_mask = -1;
+  if (!d->a_mn && !d->b_mn) return launch_tf32_major<false, false>(d, bn, stages, ta, tb, p, e, stream);
+  if (!d->a_mn && d->b_mn) return launch_tf32_major<false, true>(d, bn, stages, ta, tb, p, e, stream);
+  if (d->a_mn && !d->b_mn) return launch_tf32_major<true, false>(d, bn, stages, ta, tb, p, e, stream);
+  return launch_tf32_major<true, true>(d, bn, stages, ta, tb, p, e, stream);
+}
+
 template <bool STAGED>
 int launch_staged(const dx_gemm_desc* d, int bn, int stages, int ctas, const CUtensorMap& ta, const CUtensorMap& tb,
                   const CUtensorMap& tr, const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
@@ -105,6 +155,7 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
                       cudaStream_t stream) {
   int rc = get_encode_fn();
   if (rc) return rc;
+  if (d->in_dtype == DX_F32) return launch_tf32(d, stream);
   const int batch = d->batch > 1 ? d->batch : 1;
   DX_CHECK_ARG(d->in_dtype == DX_BF16, "dx_gemm_tc: inputs must be bf16");
   DX_CHECK_ARG(((uintptr_t)d->A % 16 == 0) && ((uintptr_t)d->B % 16 == 0), "dx_gemm_tc: A/B must be 16 B aligned");

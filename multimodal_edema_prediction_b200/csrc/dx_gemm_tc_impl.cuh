@@ -100,6 +100,15 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// kind::tf32: fp32 operands in shared memory (the tensor core reads the upper 19 bits), fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -555,7 +564,7 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED, int CTAS>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED, int CTAS, bool TF32 = false>
 __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB,
                                                              const __grid_constant__ CUtensorMap tmR,
@@ -571,6 +580,13 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
   // tiles share the N tile, and each CTA fetches HALF of the B block and multicasts it into both CTAs' rings.  This is the
   // mode of the HBM-bound shapes (K <= 1024, N = dim): their L2 -> SM traffic (B re-read by every M tile) sat at the L2
   // throughput cap.
+  // TF32: fp32 operands (kind::tf32, direct epilogue, single CTA).  A k-block is still one 128 B swizzle row = 32 elements,
+  // an MN-major tile is made of 32-element (128 B) column chunks of BKE rows, one MMA consumes 8 k.
+  static_assert(!TF32 || (!STAGED && CTAS == 1), "tf32 instances use the direct epilogue on single CTAs");
+  constexpr int BKE = TF32 ? 32 : 64;          // elements per k-block
+  constexpr int CHE = TF32 ? 32 : 64;          // elements per 128 B chunk of an MN-major tile
+  constexpr int CHB = BKE * 128;               // bytes of one MN-major chunk (BKE rows x 128 B)
+  constexpr int MNK = TF32 ? 1024 : 2048;      // MN-major: smem advance per MMA (8 / 16 k-rows)
   constexpr bool PAIR = CTAS == 2, MC = CTAS == 3;
   constexpr int CL = CTAS == 1 ? 1 : 2;
   constexpr int BNL = PAIR ? BN / 2 : BN;   // B rows held in this CTA's ring
@@ -593,7 +609,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(side_full_bar + 2 * NEPI);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int num_kb = (p.K + BKE - 1) / BKE;
   const uint32_t cta_rank = CL == 2 ? cluster_ctarank() : 0;
   const int unit0 = (int)blockIdx.x / CL, ustep = (int)gridDim.x / CL;
 
@@ -625,6 +641,11 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) ran while the
+  // previous kernel of the stream was still draining; from here on its results are read.  The dependents of THIS kernel may
+  // start their own prologue as soon as SMs free up (they block at the same point until this grid has completed).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -644,7 +665,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
           mbar_wait(empty_bar + s, ph ^ 1);
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          const int k0 = kb * BK;
+          const int k0 = kb * BKE;
           if (MC) {
             // own A tile locally; own half of the B block into BOTH CTAs (the other half arrives from the peer)
             mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
@@ -682,16 +703,16 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
           } else {
             mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
             if (!A_MN) {
-              tma_load_3d(sa, &tmA, full_bar + s, k0, m0, z);  // box {64 k, 128 m, 1}
+              tma_load_3d(sa, &tmA, full_bar + s, k0, m0, z);  // box {BKE k, 128 m, 1}
             } else {
 #pragma unroll
-              for (int c = 0; c < BM / 64; ++c) tma_load_3d(sa + c * 8192, &tmA, full_bar + s, m0 + c * 64, k0, z);  // {64 m, 64 k, 1}
+              for (int c = 0; c < BM / CHE; ++c) tma_load_3d(sa + c * CHB, &tmA, full_bar + s, m0 + c * CHE, k0, z);  // {CHE m, BKE k, 1}
             }
             if (!B_MN) {
-              tma_load_3d(sb, &tmB, full_bar + s, k0, n0, z);  // box {64 k, BN n, 1}
+              tma_load_3d(sb, &tmB, full_bar + s, k0, n0, z);  // box {BKE k, BN n, 1}
             } else {
 #pragma unroll
-              for (int c = 0; c < BN / 64; ++c) tma_load_3d(sb + c * 8192, &tmB, full_bar + s, n0 + c * 64, k0, z);
+              for (int c = 0; c < BN / CHE; ++c) tma_load_3d(sb + c * CHB, &tmB, full_bar + s, n0 + c * CHE, k0, z);
             }
           }
         }
@@ -702,7 +723,8 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
       // ===== MMA issuer (the leader CTA of a pair issues for both) =====
       // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
       // a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+      constexpr uint32_t FMT = TF32 ? 2u : 1u;   // a_format / b_format: 1 = bf16, 2 = tf32
+      constexpr uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((A_MN ? 1u : 0u) << 15) |
                                  ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * (PAIR ? 2 : 1)) >> 4) << 24);
       uint32_t it = 0, tcount = 0;
       for (int unit = unit0; unit < p.total_tiles; unit += ustep, ++tcount) {
@@ -720,13 +742,14 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major: advance 16 bf16 = 32 B inside the 128 B swizzle row.
-            // MN-major: advance 16 k-rows = two 1024 B swizzle atoms.
-            const uint64_t ad = make_smem_desc(sa + (A_MN ? k * 2048 : k * 32), p.a_lbo, p.a_sbo);
-            const uint64_t bd = make_smem_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
+          for (int k = 0; k < 4; ++k) {
+            // K-major: advance 16 bf16 (8 tf32) = 32 B inside the 128 B swizzle row.
+            // MN-major: advance 16 (8) k-rows = two (one) 1024 B swizzle atoms.
+            const uint64_t ad = make_smem_desc(sa + (A_MN ? k * MNK : k * 32), p.a_lbo, p.a_sbo);
+            const uint64_t bd = make_smem_desc(sb + (B_MN ? k * MNK : k * 32), p.b_lbo, p.b_sbo);
             const uint32_t accf = (kb > kb_lo || k > 0 || ((p.fault & 1) && tcount >= 2)) ? 1u : 0u;
-            if (PAIR) umma_f16_pair(acc, ad, bd, idesc, accf);
+            if (TF32) umma_tf32(acc, ad, bd, idesc, accf);
+            else if (PAIR) umma_f16_pair(acc, ad, bd, idesc, accf);
             else umma_f16(acc, ad, bd, idesc, accf);
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
@@ -828,7 +851,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------
 // Launcher (one instantiation per tile configuration)
 // ------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED, int CTAS = 1>
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool STAGED, int CTAS = 1, bool TF32 = false>
 int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr,
                const CUtensorMap& tx, const TcParams& p, const DxEpi& e, cudaStream_t stream) {
   constexpr int CL = CTAS == 1 ? 1 : 2;
@@ -838,7 +861,7 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
     dx_set_error("dx_gemm_tc: tile config BN=%d stages=%d needs %d B of shared memory", BN, STAGES, smem);
     return DX_ERR_UNSUPPORTED;
   }
-  auto kern = dx_gemm_tc_kernel<BN, STAGES, A_MN, B_MN, STAGED, CTAS>;
+  auto kern = dx_gemm_tc_kernel<BN, STAGES, A_MN, B_MN, STAGED, CTAS, TF32>;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -860,7 +883,7 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   }
   // split-K: only for pure fp32 accumulation (dW += A^T B) when the output tiles cannot fill the machine
   pp.splits = 1;
-  const int num_kb = dx_ceil_div(d->K, BK);
+  const int num_kb = dx_ceil_div(d->K, TF32 ? 32 : BK);
   const bool pure_acc = d->accumulate && d->out_dtype == DX_F32 && !d->out2 && !d->res && !d->aux && !d->cx && !d->bias &&
                         !d->row_scale && !d->row_sumsq && !d->row_dot && d->act == DX_ACT_NONE;
   const int workers = num_sms / CL;   // CTAs, or CTA pairs
@@ -883,28 +906,40 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
     return DX_ERR_ARG;
   }
   pp.total_tiles = (int)total;
+  // programmatic stream serialization (PDL): the kernel's prologue overlaps the tail of its predecessor in the stream
+  // (griddepcontrol.wait in the kernel); DX_GEMM_PDL=0 launches with full serialization
+  static int pdl = -1;
+  if (pdl < 0) {
+    const char* env = getenv("DX_GEMM_PDL");
+    pdl = env ? (atoi(env) != 0) : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   if (CL == 2) {
     // one CTA pair (cluster of 2 = the two SMs of a TPC) per 256-row tile; persistent over min(pairs, tiles)
     const int pairs = (int)(total < workers ? total : workers);
-    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(NTHREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    DX_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, tx, pp, e));
-    return DX_OK;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  } else {
+    const int ctas_per_sm = smem <= 113 * 1024 ? 2 : 1;   // persistent grid: fill every SM, no more
+    cfg.gridDim = dim3((unsigned)(total < (long long)num_sms * ctas_per_sm ? total : (long long)num_sms * ctas_per_sm));
   }
-  const int ctas_per_sm = smem <= 113 * 1024 ? 2 : 1;   // persistent grid: fill every SM, no more
-  const int grid = (int)(total < (long long)num_sms * ctas_per_sm ? total : (long long)num_sms * ctas_per_sm);
-  kern<<<grid, NTHREADS, smem, stream>>>(ta, tb, tr, tx, pp, e);
-  DX_LAUNCH_CHECK();
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  DX_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, tx, pp, e));
   return DX_OK;
 }
 
@@ -927,6 +962,12 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
 #define DX_TC_GROUP_5(X) DX_TC_1CTA_REST(X, false, true, true)
 #define DX_TC_GROUP_6(X) DX_TC_PAIR(X, false, false, true) DX_TC_PAIR(X, false, true, true)
 #define DX_TC_GROUP_7(X) DX_TC_MCAST(X, false, false, true) DX_TC_MCAST(X, false, true, true)
+// fp32-operand (kind::tf32) instances: direct epilogue, single CTA, every operand layout
+#define DX_TC32_LAYOUT(X, A, B) X(256, 4, A, B) X(192, 4, A, B) X(128, 6, A, B) X(64, 6, A, B)
+#define DX_TC_GROUP_8(X) DX_TC32_LAYOUT(X, false, false) DX_TC32_LAYOUT(X, false, true) DX_TC32_LAYOUT(X, true, false) \
+                         DX_TC32_LAYOUT(X, true, true)
+#define DX_TC32_INSTANTIATE(BN, ST, A, B) template int launch_cfg<BN, ST, A, B, false, 1, true> DX_TC_SIG;
+#define DX_TC32_DECLARE(BN, ST, A, B) extern template int launch_cfg<BN, ST, A, B, false, 1, true> DX_TC_SIG;
 #define DX_TC_ALL_GROUPS(X) DX_TC_GROUP_0(X) DX_TC_GROUP_1(X) DX_TC_GROUP_2(X) DX_TC_GROUP_3(X) DX_TC_GROUP_4(X) \
                             DX_TC_GROUP_5(X) DX_TC_GROUP_6(X) DX_TC_GROUP_7(X)
 #define DX_TC_SIG                                                                                                      \

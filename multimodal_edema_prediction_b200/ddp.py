@@ -152,8 +152,11 @@ def shadow_of(param: torch.Tensor):
 class GradReducer:
     """Bucketed, backward-overlapped gradient all-reduce (sum; the mean's 1/world goes into the optimizer)."""
 
-    def __init__(self, flat: FlatParams, group=None, bucket_cap_mb: float = 0.0):
+    def __init__(self, flat: FlatParams, group=None, bucket_cap_mb: float = 0.0, trace: bool = False):
         self.flat, self.group = flat, group
+        # trace: per-bucket CUDA events (eager steps only) -> self.timeline(): when each bucket became ready on the compute
+        # stream and when its all-reduce started / finished, relative to start_step() — the evidence for "overlapped"
+        self.trace, self._ev, self._t0, self._comm = trace, [], None, None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.pending, self.covered, self.launched = [], [], 0
         self.bucket_cap = int(bucket_cap_mb * (1 << 20) / 4)       # elements; 0 = one bucket per notification
@@ -171,6 +174,12 @@ class GradReducer:
 
     def start_step(self):
         self.pending, self.covered, self.launched, self._held = [], [], 0, None
+        if self.trace:
+            self._ev = []
+            self._t0 = torch.cuda.Event(enable_timing=True)
+            self._t0.record()
+            if self._comm is None:
+                self._comm = torch.cuda.Stream()
 
     def _on_ready(self, prefix: str, keys=None):
         """prefix = 'time_transformers.3' ...; keys = the parameter names (ENC_KEYS subset) under it that are final now
@@ -204,9 +213,26 @@ class GradReducer:
     def _launch(self, lo, hi):
         if hi <= lo:
             return
-        self.pending.append(dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if self.trace:
+            main = torch.cuda.current_stream()
+            ready, start, end = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ready.record(main)
+            self._comm.wait_stream(main)
+            with torch.cuda.stream(self._comm):
+                start.record()
+                dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group)   # stream-ordered on _comm
+                end.record()
+            self._ev.append((lo, hi, ready, start, end))
+            self.pending.append(None)
+        else:
+            self.pending.append(dist.all_reduce(self.flat.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.covered.append((lo, hi))
         self.launched += 1
+
+    def timeline(self):
+        """[(MB, ready_ms, start_ms, end_ms)] of the last traced step (call after a device synchronisation)."""
+        return [((hi - lo) * 4 / 2 ** 20, self._t0.elapsed_time(r), self._t0.elapsed_time(s), self._t0.elapsed_time(e))
+                for lo, hi, r, s, e in self._ev]
 
     def finish(self):
         """Reduce everything that was not announced during backward (heads, perceiver, embeddings — backward has returned,
@@ -221,8 +247,11 @@ class GradReducer:
                 self._launch(pos, lo)
                 pos = hi
             self._launch(pos, self.flat.numel)
+            if self.trace:
+                torch.cuda.current_stream().wait_stream(self._comm)
             for w in self.pending:
-                w.wait()
+                if w is not None:
+                    w.wait()
         self.pending = []
         return 1.0 / self.world
 

@@ -191,7 +191,11 @@ class Model(nn.Module):
         self.pretrain_value, self.save_representation = pretrain_value, save_representation
         self.n_transformer_head, self.n_duett_layers = n_transformer_head, n_duett_layers
         self.transformer_dropout = transformer_dropout
-        self.precision = precision          # "auto" (follow torch.autocast), "bf16" or "fp32"
+        # "auto" (follow torch.autocast), "bf16" (tcgen05 kind::f16), "tf32" (fp32 storage, tcgen05 kind::tf32 contractions — the
+        # reference's SSL / fine-tune precision, duett/duett.py:9) or "fp32" (exact FFMA products: the 1e-3 parity mode)
+        if precision not in ("auto", "bf16", "tf32", "fp32"):
+            raise ValueError(f"precision must be auto / bf16 / tf32 / fp32, got {precision!r}")
+        self.precision = precision
         self.final_norm = True
         self.register_buffer("MASKED_EMBEDDING_KEY", torch.tensor(0))
         self.register_buffer("REPRESENTATION_EMBEDDING_KEY", torch.tensor(1))
@@ -409,32 +413,30 @@ class Model(nn.Module):
             if self.predict_events:
                 evs.append(int(self.rng.choice(np.arange(0, self.d_time_series_num))))
         dev = xs_ts.device
-        ar = torch.arange(B, device=dev)
-        st = torch.tensor(steps, device=dev)
-        y_ts = xs_ts[ar, st, :V].clone()
-        y_ts_masks = xs_ts[ar, st, V:2 * V].clip(0, 1)
-        x_c = xs_ts.clone()
-        x_c[ar, st, :] = 0.
-        x_c[ar, st, -1] = 1.
-        y_events, y_events_mask = [], []
-        if self.predict_events:
-            ev = torch.tensor(evs, device=dev)
-            y_events = xs_ts[ar, :, ev].clone()
-            y_events_mask = xs_ts[ar, :, ev + V].clip(0, 1)
-            x_c[ar, :, ev] = 0.
-            x_c[ar, :, ev + V] = -1.
+        if any(st >= xs_ts.shape[1] for st in steps):
+            raise IndexError("pretrain_prep_batch: a sample has fewer than 2 timesteps")      # the reference's xs_ts[i][step] raises
+        # the draws go up as ONE small pinned index block ([2,B] int32 + [B,V] uint8) and one kernel does the selection
+        # (duett/duett.py:198-233: targets, masked copy, event column, variable dropout) — SURVEY §8f-2
+        keep = None
         if self.pretrain_dropout > 0:
-            keep = torch.tensor(self.rng.random((batch_size, V)) > self.pretrain_dropout, device=dev)
-            keep = torch.logical_or(1 - y_ts_masks, keep)
-            keep = torch.cat((keep.tile(1, 2), torch.ones((batch_size, 1), device=dev)), dim=1)
-            x_c = x_c * torch.logical_or(keep.unsqueeze(1), x_c == -1)
+            keep = np.ascontiguousarray(self.rng.random((batch_size, V)) > self.pretrain_dropout).view(np.uint8)
+        idx = torch.tensor([steps, evs if self.predict_events else [0] * B], dtype=torch.int32)
+        if dev.type == "cuda":
+            idx = idx.pin_memory().to(dev, non_blocking=True)
+            keep_d = None if keep is None else torch.from_numpy(keep).pin_memory().to(dev, non_blocking=True)
+        else:
+            keep_d = None if keep is None else torch.from_numpy(keep)
+        x_c, y_ts, y_ts_masks, y_events, y_events_mask = ops.ssl_mask(
+            xs_ts.float().contiguous(), idx[0], idx[1] if self.predict_events else None, keep_d)
+        if not self.predict_events:
+            y_events, y_events_mask = [], []
         return (xs_static, x_c, xs_times, n_timesteps), y_ts, y_ts_masks, y_events, y_events_mask
 
     # ---- forward ---------------------------------------------------------------------------------------------------
     def _act_dtype(self):
         if self.precision == "bf16":
             return torch.bfloat16
-        if self.precision == "fp32":
+        if self.precision in ("fp32", "tf32"):
             return torch.float32
         if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
             return torch.bfloat16
@@ -458,7 +460,7 @@ class Model(nn.Module):
                     add(f"{kind}_transformers.{l}.{k}", getattr(enc, k))
         spec = dict(names=names, d=self.d_embedding, V=self.d_time_series_num, T=None, n_layers=self.n_duett_layers,
                     heads=self.n_transformer_head, act_dtype=at, training=self.training, final_norm=self.final_norm,
-                    emb_rm=e.bn_rm, emb_rv=e.bn_rv, dropout=float(self.transformer_dropout))
+                    emb_rm=e.bn_rm, emb_rv=e.bn_rv, dropout=float(self.transformer_dropout), tf32=self.precision == "tf32")
         return spec, params
 
     def encode(self, x):

@@ -15,7 +15,7 @@ import torch
 
 
 class CudaGraphStep:
-    def __init__(self, fn, static_inputs: dict, warmup: int = 3):
+    def __init__(self, fn, static_inputs: dict, warmup: int = 3, pool=None):
         self.fn, self.static = fn, static_inputs
         self.graph = None
         # Warm-up on the CURRENT stream (lazy allocations, cudaFuncSetAttribute).  The usual side-stream warm-up makes the
@@ -26,7 +26,7 @@ class CudaGraphStep:
         del out                          # no eager autograd graph may be released in the middle of the capture
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, pool=pool):      # pool: share another graph's memory pool (graphs never replayed concurrently)
             self.out = fn()
         self.graph = g
 

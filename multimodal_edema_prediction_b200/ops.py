@@ -40,19 +40,58 @@ def _chk(t, dtype=None, contiguous=True):
     return t
 
 
-PROFILE = None   # bench.py sets this to a list: every GEMM launch then records (tag, flops, bytes, start_evt, end_evt)
+PROFILE = None   # bench.py sets this to a list: every GEMM / attention launch then records (kind, tag, flops, bytes, start_evt, end_evt)
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(e0, kind, tag, flops, nbytes):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    PROFILE.append((kind, tag, flops, nbytes, e0, e1))
+
+
+TF32 = False     # fp32-operand GEMMs on tcgen05 kind::tf32 instead of exact FFMA (set through tf32_mode)
+
+
+class tf32_mode:
+    """with ops.tf32_mode(True): every fp32 dx_gemm issued inside may use the tensor cores (kind::tf32) — the "tf32" precision
+    of the modules = the reference's own SSL / fine-tune precision (torch.set_float32_matmul_precision('high'),
+    duett/duett.py:9).  The exact FFMA mode ("fp32") stays the 1e-3 parity mode."""
+
+    def __init__(self, on):
+        self.on = bool(on)
+
+    def __enter__(self):
+        global TF32
+        self.prev, TF32 = TF32, self.on
+        return self
+
+    def __exit__(self, *a):
+        global TF32
+        TF32 = self.prev
 
 
 def gemm_(a, b, **kw):
     global _launches
     _launches += 1
+    if TF32 and a.dtype == torch.float32 and "tf32" not in kw:
+        kw["tf32"] = True
     if PROFILE is None:
         return gemm(a, b, **kw)
     a_mn, b_mn = kw.get("a_mn", False), kw.get("b_mn", False)
     G = a.shape[0] if a.dim() == 3 else 1
     M, K = (a.shape[-1], a.shape[-2]) if a_mn else (a.shape[-2], a.shape[-1])
     N = b.shape[-1] if b_mn else b.shape[-2]
-    tc = a.dtype == torch.bfloat16 and not kw.get("force_simt", False)
+    tc = (a.dtype == torch.bfloat16 or kw.get("tf32", False)) and not kw.get("force_simt", False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     gemm(a, b, **kw)
@@ -236,8 +275,11 @@ def attn_fwd(q, k, v, heads, drop=None):
         t_, bs, rs = _view3(t)
         args += [_p(t_), bs, rs]
     dp, dseed = (float(drop[0]), int(drop[1])) if drop else (0.0, 0)
+    ev = _prof_begin()
     _call("dx_attn_fwd", *args, _p(lse), B, heads, Sq, Sk, dh, _dt(q), dp, dseed,
           _p(drop_step_counter(q.device)) if drop else None)
+    _prof_end(ev, "attn_fwd", f"B{B}xH{heads}xS{Sq}x{Sk}xdh{dh}", 4.0 * B * heads * Sq * Sk * dh,
+              (q.numel() + k.numel() + v.numel() + o.numel()) * q.element_size())
     return o, lse
 
 
@@ -251,8 +293,11 @@ def attn_bwd(q, k, v, o, go, lse, heads, dq, dk, dv, drop=None):
         t_, bs, rs = _view3(t)
         args += [_p(t_), bs, rs]
     dp, dseed = (float(drop[0]), int(drop[1])) if drop else (0.0, 0)
+    ev = _prof_begin()
     _call("dx_attn_bwd", *args, _p(lse), _p(Dws), B, heads, Sq, Sk, dh, _dt(q), dp, dseed,
           _p(drop_step_counter(q.device)) if drop else None)
+    _prof_end(ev, "attn_bwd", f"B{B}xH{heads}xS{Sq}x{Sk}xdh{dh}", 10.0 * B * heads * Sq * Sk * dh,
+              (2 * q.numel() + 2 * k.numel() + 2 * v.numel() + 2 * o.numel()) * q.element_size())
 
 
 # ---- embedding ---------------------------------------------------------------------------------------------------------
@@ -513,6 +558,27 @@ def bin_events(slot, vals, cnts, row_start, means, stds, T):
     x = torch.empty((B, T, 2 * V), device=vals.device, dtype=torch.float32)
     _call("dx_bin_events", _p(slot), _p(vals), _p(cnts), _p(row_start), _p(means), _p(stds), B, T, V, _p(x))
     return x
+
+
+def ssl_mask(xs, step, ev, keep):
+    """Model.pretrain_prep_batch's masking in one launch (duett/duett.py:189-237).  xs [B,T,2V+1] f32, step / ev [B] int32
+    (ev None: no event prediction), keep [B,V] uint8 or None -> (x_c, y_ts, y_ts_masks, y_events, y_events_mask)."""
+    _chk(xs, torch.float32); _chk(step, torch.int32)
+    B, T, C = xs.shape
+    V = (C - 1) // 2
+    xc = torch.empty_like(xs)
+    y_ts = torch.empty((B, V), device=xs.device, dtype=torch.float32)
+    y_mask = torch.empty((B, V), device=xs.device, dtype=torch.float32)
+    y_ev = y_ev_mask = None
+    if ev is not None:
+        _chk(ev, torch.int32)
+        y_ev = torch.empty((B, T), device=xs.device, dtype=torch.float32)
+        y_ev_mask = torch.empty((B, T), device=xs.device, dtype=torch.float32)
+    if keep is not None:
+        _chk(keep, torch.uint8)
+        assert keep.shape == (B, V)
+    _call("dx_ssl_mask", _p(xs), _p(step), _p(ev), _p(keep), B, T, V, _p(xc), _p(y_ts), _p(y_mask), _p(y_ev), _p(y_ev_mask))
+    return xc, y_ts, y_mask, y_ev, y_ev_mask
 
 
 def binary_auc(logits, labels, apply_sigmoid=True):

@@ -29,7 +29,7 @@ def _gelu_grad(x):
 
 def gemm_(a, b, *, a_mn=False, b_mn=False, out=None, out2=None, accumulate=False, act=ACT_NONE, act_dtype=None,
           row_scale=None, row_scale2=None, bias=None, res=None, aux=None, aux_bias=None, cx=None, coef_num=None,
-          coef_den=None, row_sumsq=None, row_dot=None, force_simt=False, split_k=0):
+          coef_den=None, row_sumsq=None, row_dot=None, force_simt=False, split_k=0, tf32=False):
     A = a.float().transpose(-1, -2) if a_mn else a.float()
     Bm = b.float().transpose(-1, -2) if b_mn else b.float()
     v = A @ Bm.transpose(-1, -2)
@@ -459,6 +459,30 @@ def adamw(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale_dev=None, g
         shadow.copy_(p)
 
 
+def ssl_mask(xs, step, ev, keep):
+    """Contract of dx_ssl_mask = the reference's index chain (duett/duett.py:198-233), written with torch indexing."""
+    B, T, C = xs.shape
+    V = (C - 1) // 2
+    ar, st = torch.arange(B), step.long()
+    y_ts = xs[ar, st, :V].clone()
+    y_mask = xs[ar, st, V:2 * V].clip(0, 1)
+    xc = xs.clone()
+    xc[ar, st, :] = 0.
+    xc[ar, st, -1] = 1.
+    y_ev = y_ev_mask = None
+    if ev is not None:
+        e = ev.long()
+        y_ev = xs[ar, :, e].clone()
+        y_ev_mask = xs[ar, :, e + V].clip(0, 1)
+        xc[ar, :, e] = 0.
+        xc[ar, :, e + V] = -1.
+    if keep is not None:
+        k = torch.logical_or(1 - y_mask, keep.bool())
+        k = torch.cat((k.tile(1, 2), torch.ones((B, 1))), dim=1)
+        xc = xc * torch.logical_or(k.unsqueeze(1), xc == -1)
+    return xc, y_ts, y_mask, y_ev, y_ev_mask
+
+
 def cast_into(x, y):
     y.copy_(x)
     return y
@@ -496,7 +520,7 @@ EMULATED = ["binary_auc", "sum_n", "dropout", "rowdot_bias", "gemm_", "relayout_
             "attn_fwd", "attn_bwd", "embed_fwd", "embed_bwd", "bn2d_fwd", "bn2d_bwd", "layernorm_fwd", "layernorm_bwd",
             "mean_rows", "mean_rows_bwd", "gather_vec", "scatter_vec", "kd_loss", "bce_logits", "masked_mse_bce",
             "masked_bce_cols", "aux_residual_kl", "require_device", "act_bwd", "act_fwd", "scale_dev", "sum_div_acc", "fusion_logits",
-            "fusion_logits_bwd", "adamw", "sumsq", "clip_factor", "cast_into"]
+            "fusion_logits_bwd", "adamw", "sumsq", "clip_factor", "cast_into", "ssl_mask"]
 
 
 def install(monkeypatch):

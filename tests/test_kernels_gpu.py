@@ -400,6 +400,27 @@ def test_bin_events_bit_exact_vs_reference_golden(ops):
     bad.loc[0, "slot_idx"] = -T - 1
     with pytest.raises(IndexError):
         md.build_stay_tensor(bad, means, stds, T, all_vars, all_counts)
+    # The Dataset as the reference's training scripts use it: DataLoader workers + pin_memory + the collate function
+    # (duett/train_duett_ssl.py:137).  __getitem__ is host-only (StayRows); the batch is binned by ONE launch in the main
+    # process when the model's feats_to_input meets it.
+    from multimodal_edema_prediction_b200.duett.duett import Model
+    B = len(frames)
+    icu = pd.concat([f.assign(stay_id=100 + b) for b, f in enumerate(frames)], ignore_index=True)
+    static = pd.DataFrame({"stay_id": [100 + b for b in range(B)], "age_at_intime": np.linspace(30, 80, B), "s0": 1.0, "s1": 0.0,
+                           "label": [float(b % 2) for b in range(B)]})
+    meta = {"N_TIMESTEPS": T, "LABEL_COL": "label", "age_mean": 55.0, "age_std": 10.0, "ONEHOT_STATIC": ["s0", "s1"],
+            "means": means, "stds": stds, "ALL_VARS": all_vars, "ALL_COUNTS": all_counts, "D_STATIC": 3}
+    ds = md.MIMICDataset([100 + b for b in range(B)], icu, static, meta)
+    item = ds[0]
+    assert isinstance(item[0][0], md.StayRows) and not torch.is_tensor(item[0][0])
+    dl = torch.utils.data.DataLoader(ds, batch_size=B, shuffle=False, num_workers=2, pin_memory=True,
+                                     collate_fn=md.collate_into_seqs)
+    (xs_ts, xs_static, times), ys = next(iter(dl))
+    model = Model(3, V, 1, d_embedding=8, masked_transform_timesteps=T, max_len=T, n_duett_layers=1, pretrain=False,
+                  precision="fp32").cuda().eval()
+    x_static_d, x_ts_d, x_times_d, n_ts = model.feats_to_input((xs_ts, xs_static, times), B)
+    assert x_ts_d.is_cuda and np.array_equal(x_ts_d[:, :, :-1].cpu().numpy(), G["x"], equal_nan=True)
+    assert x_static_d.shape == (B, 3) and x_times_d.shape == (B, T) and n_ts == [T] * B and len(ys) == B
 
 
 @pytest.mark.parametrize("dt", DT)
@@ -529,3 +550,73 @@ def test_evaluate_dual_pathology_on_device(ops):
         assert abs(r["ts_auroc"] - roc_auc_score(y[m, k], sig(pv[m, K + k]))) < 1e-6
         assert abs(r["img_auprc"] - average_precision_score(y[m, k], sig(pv[m, k]))) < 1e-6
     assert res["n"] == 200 and res["main_auroc"] == res["main_auroc"]
+
+
+# ---- fp32 operands on the tensor cores (tcgen05 kind::tf32): the reference's SSL / fine-tune precision ---------------------
+TF32_TOL = 3e-3     # tf32 keeps 10 mantissa bits of each operand (relative 2^-11..2^-10 per product), fp32 accumulate
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_tf32_layouts(ops, a_mn, b_mn):
+    M, N, K = 520, 392, 264
+    a = rnd(*((K, M) if a_mn else (M, K)), seed=101)
+    b = rnd(*((K, N) if b_mn else (N, K)), seed=102)
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm_(a, b, a_mn=a_mn, b_mn=b_mn, out=out, tf32=True)
+    ref = torch.empty(M, N)
+    E.gemm_(*cpu(a, b), a_mn=a_mn, b_mn=b_mn, out=ref)
+    e = rel(out, ref)
+    assert 1e-6 < e < TF32_TOL, e               # > 1e-6: the tensor-core path really ran (FFMA would be ~1e-7)
+    exact = torch.empty(M, N, device="cuda")
+    ops.gemm_(a, b, a_mn=a_mn, b_mn=b_mn, out=exact)          # default fp32 mode stays exact
+    assert rel(exact, ref) < 1e-5
+    acc = torch.full((M, N), 2.0, device="cuda")
+    ops.gemm_(a, b, a_mn=a_mn, b_mn=b_mn, out=acc, accumulate=True, tf32=True)
+    assert rel(acc - 2.0, ref) < TF32_TOL
+
+
+def test_gemm_tf32_fused_epilogues_and_grouped(ops):
+    M, N, K = 300, 264, 136
+    a, b = rnd(M, K, seed=103), rnd(N, K, seed=104, scale=0.1)
+    rs = torch.rand(M, device="cuda") + 0.5
+    bias, res = rnd(N, seed=105), rnd(M, N, seed=106)
+    out, out2 = torch.empty(M, N, device="cuda"), torch.empty(M, N, device="cuda")
+    ops.gemm_(a, b, out=out, out2=out2, row_scale=rs, bias=bias, act=ops.ACT_GELU, act_dtype=torch.float32, tf32=True)
+    r_out, r_out2 = torch.empty(M, N), torch.empty(M, N)
+    E.gemm_(*cpu(a, b), out=r_out, out2=r_out2, row_scale=rs.cpu(), bias=bias.cpu(), act=ops.ACT_GELU)
+    assert rel(out, r_out) < TF32_TOL and rel(out2, r_out2) < TF32_TOL
+    rowsq = torch.zeros(M, device="cuda")
+    ops.gemm_(a, b, out=out, bias=bias, res=res, row_sumsq=rowsq, act_dtype=torch.float32, tf32=True)
+    r_rowsq = torch.zeros(M)
+    E.gemm_(*cpu(a, b), out=r_out, bias=bias.cpu(), res=res.cpu(), row_sumsq=r_rowsq)
+    assert rel(out, r_out) < TF32_TOL and rel(rowsq, r_rowsq) < TF32_TOL
+    # grouped mode on the strided views of the embedding (64 -> d and its dW)
+    G, R, d, H = 5, 300, 24, 64
+    psi = rnd(R, G, d, seed=107)
+    av = psi.permute(1, 0, 2)
+    hn, w = rnd(G, R, H, seed=108), rnd(G, d, H, seed=109, scale=0.3)
+    outp = torch.zeros(R, G, d, device="cuda")
+    ops.gemm_(hn, w, out=outp.permute(1, 0, 2), bias=rnd(G, d, seed=110), act_dtype=torch.float32, tf32=True)
+    want = torch.einsum("grh,gdh->grd", hn, w) + rnd(G, d, seed=110)[:, None, :]
+    assert rel(outp.permute(1, 0, 2), want) < TF32_TOL
+    dw = torch.ones(G, d, H, device="cuda")
+    ops.gemm_(av, hn, a_mn=True, b_mn=True, out=dw, accumulate=True, tf32=True)
+    assert rel(dw - 1.0, torch.einsum("grd,grh->gdh", av, hn)) < TF32_TOL
+
+
+def test_gemm_tf32_production_shape_multi_tile(ops):
+    """33 024 x 512 x 4 224 (FFN-in, event axis) and its dW in fp32 storage: several tiles per persistent CTA, checked per
+    128 x 256 tile against torch's fp32 matmul."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    M, N, K = 33024, 512, 4224
+    a, b = rnd(M, K, seed=111), rnd(N, K, seed=112, scale=0.02)
+    out = torch.empty(M, N, device="cuda")
+    ops.gemm_(a, b, out=out, bias=rnd(N, seed=113), act_dtype=torch.float32, tf32=True)
+    ref = a @ b.t() + rnd(N, seed=113)[None]
+    assert rel(out, ref) < TF32_TOL
+    d = ((out - ref) ** 2).reshape(M // 128, 128, N // 256, 256).sum((1, 3))
+    r = (ref ** 2).reshape(M // 128, 128, N // 256, 256).sum((1, 3))
+    assert float((d / r).sqrt().max()) < 2 * TF32_TOL
+    dw = torch.zeros(N, K, device="cuda")
+    ops.gemm_(out, a, a_mn=True, b_mn=True, out=dw, accumulate=True, tf32=True)
+    assert rel(dw, out.t() @ a) < TF32_TOL

@@ -145,7 +145,7 @@ def _supervised_vs_oracle(cfg, B, mode, tol, seed, name):
         assert f_z < 3 * tol and f_l < tol and f_g < 3 * tol, ("free-running fp32", f_z, f_l, f_g)
 
 
-def _student_vs_oracle(cfg, B, mode, tol, seed, name):
+def _student_vs_oracle(cfg, B, mode, tol, seed, name, check_tokens=False):
     """The same backbone under the KD student head (mean pooling -> Linear-GELU-Linear, no BatchNorm over the batch) and
     StudentKDLoss: every quantity at the plain north-star bound (logits get 2x in bf16: they are ~0.1 in magnitude with
     a common-mode part)."""
@@ -155,6 +155,7 @@ def _student_vs_oracle(cfg, B, mode, tol, seed, name):
     batch = O.synth_batch(cfg, B, seed=4321 + seed)
     xs_static, xs_ts, xs_times, _ = O.feats_to_input(batch["x_ts"], batch["x_static"], batch["bin_ends"], cfg.T)
     Pl, Hl = _leaf(P), _leaf(H)
+    tokens_ref = O.encode(Pl, cfg, xs_static, xs_ts, xs_times, training=True).detach() if check_tokens else None
     z_ref = O.student_forward(Pl, Hl, cfg, xs_static, xs_ts, xs_times, pool="mean")
     z_t = torch.randn(B, generator=torch.Generator().manual_seed(5)) * 1.5
     L_ref = O.student_kd_loss(z_ref, z_t, batch["y"], 4.0, 0.5, None)
@@ -167,6 +168,12 @@ def _student_vs_oracle(cfg, B, mode, tol, seed, name):
     sd.update(H)
     student.load_state_dict(sd, strict=True)
     student.cuda().train()
+    e_tok = 0.0
+    if check_tokens:
+        x = (batch["x_ts"], batch["x_static"], list(batch["bin_ends"]))
+        e_tok = rel(duett.encode(duett.feats_to_input(x, B)).float().cpu(), tokens_ref)
+        student.load_state_dict(sd)
+        student.cuda()
     z = student(batch["x_ts"], batch["x_static"], list(batch["bin_ends"]))
     losses = StudentKDLoss(kd_T=4.0, kd_alpha=0.5)(z, z_t.cuda(), batch["y"].cuda())
     losses["total"].backward()
@@ -176,7 +183,8 @@ def _student_vs_oracle(cfg, B, mode, tol, seed, name):
     got = _ref_keyed_grads(student)
     e_z, e_l = rel(z.detach().cpu(), z_ref.detach()), rel(losses["total"].detach().cpu(), L_ref["total"].detach())
     e_g = _global_grad_err({k: got[k] for k in want}, want)
-    record(name, mode, logits=e_z, loss=e_l, grads_global=e_g, B=B)
+    record(name, mode, tokens=e_tok, logits=e_z, loss=e_l, grads_global=e_g, B=B)
+    assert e_tok < tol, ("encoder tokens", e_tok)
     assert e_l < tol, ("loss", e_l)
     assert e_z < tol * (1 if mode == "fp32" else 2), ("logits", e_z)
     assert e_g < tol, ("all gradients, global relative L2", e_g)
@@ -199,9 +207,11 @@ def test_c2_shape_student_kd_vs_oracle(mode, tol):
 @pytest.mark.parametrize("mode,tol", MODES)
 def test_c5_shape_vs_oracle(mode, tol):
     """BASELINE configs[4] stress shape (T=128, V=512, d=256; E=33 024, E'=131 328, dh=128) at B=2 against the CPU oracle
-    (replaces the bf16-vs-fp32 self-comparison of tests/c5_smoke.py)."""
+    (replaces the bf16-vs-fp32 self-comparison of tests/c5_smoke.py): backbone + KD student head + StudentKDLoss, every
+    quantity at the plain bound.  (The supervised head's BatchNorm over a batch of TWO samples is degenerate — x_hat = +-1
+    whatever the input — so that head is exercised at C2/B=32 above, not here.)"""
     cfg = O.DuettConfig(d_static_num=24, d_time_series_num=512, n_timesteps=128, d_embedding=256, n_layers=2)
-    _supervised_vs_oracle(cfg, 2, mode, tol, seed=9, name="c5_supervised")
+    _student_vs_oracle(cfg, 2, mode, tol, seed=9, name="c5_student_kd", check_tokens=True)
 
 
 @pytest.mark.parametrize("mode,tol", MODES)
@@ -283,3 +293,52 @@ def test_auroc_fixed_eval_set_4096(mode):
         assert d <= one_pair * 5.0001, (res["auroc"], a_ref, d / one_pair, "swapped pairs")
     else:
         assert d < 5e-3, (res["auroc"], a_ref)
+
+
+def test_tf32_mode_student_step_vs_oracle():
+    """precision="tf32": fp32 storage, contractions on tcgen05 kind::tf32 — the reference's SSL / fine-tune precision
+    (torch.set_float32_matmul_precision('high'), duett/duett.py:9).  C1-shaped model, B=8, against the fp32 CPU oracle at a
+    TF32-sized bound: 10 mantissa bits per operand -> ~1e-3 per contraction; 5e-3 on tokens / loss, 2e-2 on gradients
+    (between the exact-fp32 mode's 1e-3 and the bf16 mode's 2e-2)."""
+    cfg = O.DuettConfig(d_static_num=24, d_time_series_num=128, n_timesteps=32, d_embedding=64, n_layers=2)
+    from multimodal_edema_prediction_b200.loss.losses_duett import StudentKDLoss
+    from multimodal_edema_prediction_b200.models.main_architecture_duett import DuettFeatureExtractor, StudentModel
+    B = 8
+    P, H = O.init_params(cfg, seed=31), O.init_student_head(cfg, seed=32)
+    batch = O.synth_batch(cfg, B, seed=555)
+    xs_static, xs_ts, xs_times, _ = O.feats_to_input(batch["x_ts"], batch["x_static"], batch["bin_ends"], cfg.T)
+    Pl, Hl = _leaf(P), _leaf(H)
+    tokens_ref = O.encode(Pl, cfg, xs_static, xs_ts, xs_times, training=True).detach()
+    z_ref = O.student_forward(Pl, Hl, cfg, xs_static, xs_ts, xs_times, pool="mean")
+    z_t = torch.randn(B, generator=torch.Generator().manual_seed(5)) * 1.5
+    L_ref = O.student_kd_loss(z_ref, z_t, batch["y"], 4.0, 0.5, None)
+    L_ref["total"].backward()
+    res = {}
+    for mode in ("tf32", "fp32"):
+        duett = DuettFeatureExtractor(cfg.d_static_num, cfg.V, 1, d_embedding=cfg.d_embedding, n_duett_layers=cfg.n_layers,
+                                      masked_transform_timesteps=cfg.T, max_len=cfg.T, d_feedforward=cfg.d_feedforward,
+                                      pretrain=False, precision=mode)
+        student = StudentModel(duett, pool="mean", head_hidden=128, head_dropout=0.0)
+        sd = {"duett." + k: v for k, v in P.items()}
+        sd.update(H)
+        student.load_state_dict(sd, strict=True)
+        student.cuda().train()
+        x = (batch["x_ts"], batch["x_static"], list(batch["bin_ends"]))
+        tok = duett.encode(duett.feats_to_input(x, B))
+        assert tok.dtype == torch.float32
+        student.load_state_dict(sd)
+        student.cuda()
+        z = student(*x)
+        losses = StudentKDLoss(kd_T=4.0, kd_alpha=0.5)(z, z_t.cuda(), batch["y"].cuda())
+        losses["total"].backward()
+        torch.cuda.synchronize()
+        want = {"duett." + k: v.grad for k, v in Pl.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+        want.update({k: v.grad for k, v in Hl.items()})
+        got = _ref_keyed_grads(student)
+        res[mode] = (rel(tok.cpu(), tokens_ref), rel(losses["total"].detach().cpu(), L_ref["total"].detach()),
+                     _global_grad_err({k: got[k] for k in want}, want))
+        record("c1_student_kd_" + mode, mode, tokens=res[mode][0], loss=res[mode][1], grads_global=res[mode][2], B=B)
+    t, l, g = res["tf32"]
+    assert t < 5e-3 and l < 5e-3 and g < 2e-2, res
+    assert res["tf32"][0] > 3 * res["fp32"][0], ("the tf32 mode must actually run on the tf32 tensor-core path", res)
+    assert res["fp32"][0] < 1e-3 and res["fp32"][2] < 1e-3, res
