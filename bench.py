@@ -409,6 +409,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"],
+                    help="bf16 (default: tcgen05 kind::f16), tf32 (fp32 storage, tcgen05 kind::tf32: the reference's SSL precision), "
+                         "fp32 (exact FFMA parity mode)")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (experiments; the line then says so)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="samples per CPU-baseline step (default 16; c1: 32; c5: 2)")
     ap.add_argument("--force-port", action="store_true", help="reference arm: use the oracle port even if /root/reference exists")
@@ -439,7 +442,7 @@ def main():
     if cfg["scaling"] == "strong" and cfg["B"] % world:
         raise SystemExit(f"global batch {cfg['B']} does not split over {world} ranks")
     B = args.batch or (cfg["B"] if cfg["scaling"] == "weak" else cfg["B"] // world)
-    wl = Workload(cfg, device)
+    wl = Workload(cfg, device, precision=args.precision)
     w = cfg["dims"]
     nb = 4 if cfg["key"] != "c5" else 2                # distinct synthetic batches, cycled
     host = [synth_host_batch(B, 1234 + 17 * rank + i, w, with_cxr=wl.task == "kd") for i in range(nb)]
@@ -594,11 +597,14 @@ def main():
 
     # ---- parity of the measured configuration: graph-replayed bf16 step vs the eager fp32-mode step, same weights/batch ----
     parity = None
-    if not args.no_parity_check and world == 1:      # single-process check (it builds a replica and steps it without collectives)
+    if not args.no_parity_check and world == 1 and args.precision == "bf16":      # single-process check (it builds a replica and steps it without collectives)
         parity = parity_check(cfg, wl, gstep, dev_batches[0], device)
 
     if rank == 0:
         pk = peaks()
+        if args.precision == "tf32":      # kind::tf32 runs at half the bf16 tensor rate (nominal 1.1 vs 2.25 PFLOP/s dense)
+            pk = dict(pk, bf16_tflops_sustained=pk["bf16_tflops_sustained"] / 2, bf16_tflops=pk["bf16_tflops"] / 2,
+                      source=pk["source"] + " bf16 peak / 2 (tf32 tensor rate)")
         value = world * B * args.steps / (ms / 1e3)
         e2e = world * B * args.steps / (ms_e2e / 1e3)
         # ---- roofline of the tcgen05 GEMM kernel (dominant kernel family) ---------------------------------------------
@@ -673,7 +679,7 @@ def main():
         fl = train_flops_per_sample(w, wl.task)
         out = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic",
             "config": dict(config_dict(cfg, world, B),
                            l2="working set >> 126 MB L2 (every residual-stream tensor alone exceeds it), distinct input batches cycled"),

@@ -88,6 +88,11 @@ typedef struct dx_gemm_desc {
 
 int dx_gemm(const dx_gemm_desc* d, void* stream);
 
+/* Data-parallel runs: the persistent tcgen05 grids leave n SMs (even) free for the NCCL kernels of the gradient all-reduce that
+ * overlaps the backward pass (training_duett/trainer.py:217-218 / Lightning DDP bucket all-reduce).  Returns the previous n.
+ * Environment default: DX_GEMM_SM_RESERVE. */
+int dx_gemm_reserve_sms(int n);
+
 /*
  * Test hook for bring-up: same as dx_gemm on the tcgen05 path but with the shared-memory
  * matrix-descriptor fields overridden (lbo/sbo in bytes for A and B; <0 keeps the built-in value).

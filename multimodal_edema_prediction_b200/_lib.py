@@ -89,6 +89,8 @@ def _declare(L: C.CDLL) -> None:
     L.dx_gemm.restype = C.c_int
     L.dx_gemm_tc_debug.argtypes = [C.POINTER(GemmDesc)] + [C.c_int32] * 6 + [C.c_void_p]
     L.dx_gemm_tc_debug.restype = C.c_int
+    L.dx_gemm_reserve_sms.argtypes = [C.c_int]
+    L.dx_gemm_reserve_sms.restype = C.c_int
     from . import _decl
     _decl.declare(L)
 

@@ -4,6 +4,7 @@
 #include "../../include/duett_b200.h"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[1024] = "";
 
@@ -18,7 +19,25 @@ int dx_gemm_simt_launch(const dx_gemm_desc* d, cudaStream_t stream);
 int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int a_sbo, int b_lbo, int b_sbo,
                       cudaStream_t stream);
 
+static int g_reserved_sms = -1;
+int dx_gemm_reserved_sms() {
+  if (g_reserved_sms < 0) {
+    const char* env = getenv("DX_GEMM_SM_RESERVE");
+    g_reserved_sms = env ? atoi(env) : 0;
+    if (g_reserved_sms < 0) g_reserved_sms = 0;
+  }
+  return g_reserved_sms;
+}
+
 extern "C" {
+
+/* Persistent tcgen05 GEMM grids use (#SMs - n) CTAs (n even) from now on: leaves SMs to a collective that runs concurrently
+ * with the backward pass (ddp.GradReducer sets it for world > 1).  Returns the previous value. */
+int dx_gemm_reserve_sms(int n) {
+  const int prev = dx_gemm_reserved_sms();
+  g_reserved_sms = n < 0 ? 0 : (n & ~1);
+  return prev;
+}
 
 const char* dx_last_error(void) { return g_err; }
 int dx_version(void) { return 100; }

@@ -8,6 +8,8 @@
 #include "dx_common.cuh"
 #include "../../include/duett_b200.h"
 
+int dx_gemm_reserved_sms();   // dx_api.cu
+
 struct DxEpi {
   int M, N;
   void* out; long long ldo; int out_dtype; int accumulate;

@@ -31,14 +31,15 @@ int get_encode_fn() {
 // 3-D bf16 tensor map: dim0 = contiguous (size inner), dim1 = rows (size outer, stride ld elements),
 // dim2 = batch (stride bs elements).
 int make_tmap(CUtensorMap* map, const void* base, long long inner, long long outer, long long ld, int batch, long long bs,
-              int box_inner, int box_outer, int esz = 2) {
+              int box_inner, int box_outer, int esz = 2, bool atom32 = false) {
   cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(batch > 1 ? batch : 1)};
   cuuint64_t gstride[2] = {(cuuint64_t)ld * esz, (cuuint64_t)(batch > 1 ? bs * esz : ld * esz)};
   cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_encode(map, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                         const_cast<void*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     dx_set_error("cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld ld=%lld batch=%d bs=%lld box=%dx%d base=%p",
@@ -115,18 +116,22 @@ int launch_tf32(const dx_gemm_desc* d, cudaStream_t stream) {
   CUtensorMap ta, tb;
   int rc;
   if (!d->a_mn) rc = make_tmap(&ta, d->A, d->K, d->M, d->lda, batch, d->a_bs, BKE, BM, 4);
-  else rc = make_tmap(&ta, d->A, d->M, d->K, d->lda, batch, d->a_bs, CHE, BKE, 4);
+  else rc = make_tmap(&ta, d->A, d->M, d->K, d->lda, batch, d->a_bs, CHE, BKE, 4, true);
   if (rc) return rc;
   if (!d->b_mn) rc = make_tmap(&tb, d->B, d->K, d->N, d->ldb, batch, d->b_bs, BKE, bn, 4);
-  else rc = make_tmap(&tb, d->B, d->N, d->K, d->ldb, batch, d->b_bs, CHE, BKE, 4);
+  else rc = make_tmap(&tb, d->B, d->N, d->K, d->ldb, batch, d->b_bs, CHE, BKE, 4, true);
   if (rc) return rc;
   TcParams p;
   p.K = d->K;
-  // MN-major: LBO = distance between 32-element MN chunks (one {32 mn, 32 k} box = 4096 B), SBO = 8 k-rows (1024 B)
+  // K-major tf32: SWIZZLE_128B like bf16 (LBO unused, SBO = 8 rows x 128 B).
+  // MN-major tf32: the tensor core only takes the 128B swizzle with 32 B atomicity (cute: Swizzle<2,5,2>, descriptor layout
+  // type SWIZZLE_128B_BASE32B, TMA mode 128B_ATOM_32B): atoms of 4 k-rows x 128 B, so SBO = 512 B between atoms and
+  // LBO = distance between 32-element MN chunks (one {32 mn, 32 k} box = 4096 B).
   p.a_lbo = d->a_mn ? BKE * 128 : 16;
-  p.a_sbo = 1024;
+  p.a_sbo = d->a_mn ? 512 : 1024;
   p.b_lbo = d->b_mn ? BKE * 128 : 16;
-  p.b_sbo = 1024;
+  p.b_sbo = d->b_mn ? 512 : 1024;
+  if (const char* env = getenv("DX_TF32_SBO")) { if (d->a_mn) p.a_sbo = atoi(env); if (d->b_mn) p.b_sbo = atoi(env); }
   p.stage_bufs = 0;
   p.stage_ring = 1;
   p.epi_mask = -1;

@@ -213,13 +213,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (16 B chunks XOR row%8, 8-row atoms); 1 = SWIZZLE_128B_BASE32B (32 B chunks XOR row%4, 4-row
+// atoms) — the only layout the tensor core accepts for MN-major (transposed) tf32 operands; TMA writes it with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(layout & 7) << 61;
   return d;
 }
 
@@ -745,8 +748,8 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
           for (int k = 0; k < 4; ++k) {
             // K-major: advance 16 bf16 (8 tf32) = 32 B inside the 128 B swizzle row.
             // MN-major: advance 16 (8) k-rows = two (one) 1024 B swizzle atoms.
-            const uint64_t ad = make_smem_desc(sa + (A_MN ? k * MNK : k * 32), p.a_lbo, p.a_sbo);
-            const uint64_t bd = make_smem_desc(sb + (B_MN ? k * MNK : k * 32), p.b_lbo, p.b_sbo);
+            const uint64_t ad = make_smem_desc(sa + (A_MN ? k * MNK : k * 32), p.a_lbo, p.a_sbo, (TF32 && A_MN) ? 1u : 2u);
+            const uint64_t bd = make_smem_desc(sb + (B_MN ? k * MNK : k * 32), p.b_lbo, p.b_sbo, (TF32 && B_MN) ? 1u : 2u);
             const uint32_t accf = (kb > kb_lo || k > 0 || ((p.fault & 1) && tcount >= 2)) ? 1u : 0u;
             if (TF32) umma_tf32(acc, ad, bd, idesc, accf);
             else if (PAIR) umma_f16_pair(acc, ad, bd, idesc, accf);
@@ -875,12 +878,15 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   pp.fault = 0;
   if (const char* env = getenv("DX_GEMM_FAULT")) pp.fault = atoi(env);   // bit 0: injected bug; bits 1, 2: skip the side loads / the stores
   long long total = (long long)pp.tiles_n * pp.tiles_m * (d->batch > 1 ? d->batch : 1);
-  static int num_sms = 0;
-  if (!num_sms) {
+  static int dev_sms = 0;
+  if (!dev_sms) {
     int dev = 0;
     DX_CUDA(cudaGetDevice(&dev));
-    DX_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    DX_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  // SMs left free for a concurrently running collective (dx_gemm_reserve_sms): a persistent grid of exactly #SMs CTAs would
+  // otherwise wait for the SMs NCCL holds and run its last CTAs as a second wave
+  const int num_sms = dev_sms - dx_gemm_reserved_sms() > 16 ? dev_sms - dx_gemm_reserved_sms() : dev_sms;
   // split-K: only for pure fp32 accumulation (dW += A^T B) when the output tiles cannot fill the machine
   pp.splits = 1;
   const int num_kb = dx_ceil_div(d->K, TF32 ? 32 : BK);

@@ -163,9 +163,13 @@ class GradReducer:
         self._ranges = {}
         self._held = None                                         # small announced range waiting to be merged
 
-    def attach(self):
+    def attach(self, sm_reserve=None):
+        """sm_reserve: SMs the persistent GEMM grids leave free for the NCCL kernels that run concurrently with backward
+        (default: DX_GEMM_SM_RESERVE or 0; pair it with NCCL_MAX_CTAS so that NCCL stays within them)."""
         if self._on_ready not in backbone.GRAD_READY_HOOKS:
             backbone.GRAD_READY_HOOKS.append(self._on_ready)
+        if self.world > 1 and sm_reserve is not None:
+            ops.gemm_reserve_sms(sm_reserve)
         return self
 
     def detach(self):
@@ -229,6 +233,21 @@ class GradReducer:
         self.covered.append((lo, hi))
         self.launched += 1
 
+    def _unused_ranges(self):
+        if not hasattr(self, "_unused_cache"):
+            f, out, i = self.flat, [], 0
+            while i < len(f.names):
+                if f.names[i] in f.unused:
+                    j = i
+                    while j + 1 < len(f.names) and f.names[j + 1] in f.unused:
+                        j += 1
+                    out.append((f.offsets[i], f.offsets[j + 1]))
+                    i = j + 1
+                else:
+                    i += 1
+            self._unused_cache = out
+        return self._unused_cache
+
     def timeline(self):
         """[(MB, ready_ms, start_ms, end_ms)] of the last traced step (call after a device synchronisation)."""
         return [((hi - lo) * 4 / 2 ** 20, self._t0.elapsed_time(r), self._t0.elapsed_time(s), self._t0.elapsed_time(e))
@@ -241,12 +260,16 @@ class GradReducer:
             if self._held is not None:
                 self._launch(*self._held)
                 self._held = None
+            # parameters the active mode never touches (FlatParams.unused: e.g. the SSL projection heads in a supervised run —
+            # 538 MB of the stress shape's gradients) carry all-zero gradients on every rank: nothing to reduce
+            skip = list(self._unused_ranges())
             pos = 0
-            for lo, hi in sorted(self.covered):
+            for lo, hi in sorted(self.covered + skip):
                 assert lo >= pos, "overlapping all-reduce buckets"
                 self._launch(pos, lo)
                 pos = hi
             self._launch(pos, self.flat.numel)
+            self.covered = [c for c in self.covered if c not in skip]
             if self.trace:
                 torch.cuda.current_stream().wait_stream(self._comm)
             for w in self.pending:

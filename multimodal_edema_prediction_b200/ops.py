@@ -13,6 +13,11 @@ from ._lib import ACT_GELU, ACT_GELU_BWD, ACT_NONE, ACT_RELU, ACT_RELU_BWD, ACT_
 _launches = 0   # kernels-launching C calls issued (bench.py reports it as gpu_launches)
 
 
+def gemm_reserve_sms(n: int) -> int:
+    """Persistent GEMM grids leave n SMs free (for the NCCL kernels of an overlapped all-reduce); returns the previous n."""
+    return int(L.lib().dx_gemm_reserve_sms(int(n)))
+
+
 def launches() -> int:
     return _launches
 

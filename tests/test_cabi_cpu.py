@@ -16,9 +16,12 @@ def test_build_and_exports():
         assert hasattr(lib, s), s
     # every bound signature is declared in the header, and vice versa (dx_last_error / dx_version / dx_device_ok /
     # dx_gemm* are bound in _lib.py)
-    bound = set(_decl.SIGNATURES) | {"dx_last_error", "dx_version", "dx_device_ok", "dx_gemm", "dx_gemm_tc_debug"}
+    bound = set(_decl.SIGNATURES) | {"dx_last_error", "dx_version", "dx_device_ok", "dx_gemm", "dx_gemm_tc_debug",
+                                         "dx_gemm_reserve_sms"}
     assert bound == set(declared), (bound ^ set(declared))
     assert lib.dx_version() >= 100
+    prev = lib.dx_gemm_reserve_sms(9)                  # host-only setter: rounds down to an even count, returns the previous value
+    assert lib.dx_gemm_reserve_sms(prev) == 8
 
 
 def test_argument_errors_do_not_need_a_gpu():

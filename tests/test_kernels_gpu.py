@@ -404,8 +404,9 @@ def test_bin_events_bit_exact_vs_reference_golden(ops):
     # (duett/train_duett_ssl.py:137).  __getitem__ is host-only (StayRows); the batch is binned by ONE launch in the main
     # process when the model's feats_to_input meets it.
     from multimodal_edema_prediction_b200.duett.duett import Model
-    B = len(frames)
-    icu = pd.concat([f.assign(stay_id=100 + b) for b, f in enumerate(frames)], ignore_index=True)
+    keep = [b for b, f in enumerate(frames) if len(f)]          # like the reference's Dataset, a stay needs at least one event row
+    B = len(keep)
+    icu = pd.concat([frames[b].assign(stay_id=100 + i) for i, b in enumerate(keep)], ignore_index=True)
     static = pd.DataFrame({"stay_id": [100 + b for b in range(B)], "age_at_intime": np.linspace(30, 80, B), "s0": 1.0, "s1": 0.0,
                            "label": [float(b % 2) for b in range(B)]})
     meta = {"N_TIMESTEPS": T, "LABEL_COL": "label", "age_mean": 55.0, "age_std": 10.0, "ONEHOT_STATIC": ["s0", "s1"],
@@ -419,7 +420,7 @@ def test_bin_events_bit_exact_vs_reference_golden(ops):
     model = Model(3, V, 1, d_embedding=8, masked_transform_timesteps=T, max_len=T, n_duett_layers=1, pretrain=False,
                   precision="fp32").cuda().eval()
     x_static_d, x_ts_d, x_times_d, n_ts = model.feats_to_input((xs_ts, xs_static, times), B)
-    assert x_ts_d.is_cuda and np.array_equal(x_ts_d[:, :, :-1].cpu().numpy(), G["x"], equal_nan=True)
+    assert x_ts_d.is_cuda and np.array_equal(x_ts_d[:, :, :-1].cpu().numpy(), G["x"][keep], equal_nan=True)
     assert x_static_d.shape == (B, 3) and x_times_d.shape == (B, T) and n_ts == [T] * B and len(ys) == B
 
 
