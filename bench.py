@@ -464,7 +464,8 @@ def main():
             # SURVEY §8(d) also asks for the step WITHOUT the optimizer (fwd + loss + bwd + all-reduce): a second graph
             # (same memory pool: the two graphs are never replayed concurrently, and at the stress shape a second private
             # pool of saved activations would not fit next to the eager profiling pass)
-            gstep_noopt = CudaGraphStep(lambda: wl.train_step(static, optimizer=False), static, warmup=3, pool=gstep.graph.pool())
+            torch.cuda.empty_cache()
+            gstep_noopt = CudaGraphStep(lambda: wl.train_step(static, optimizer=False), static, warmup=0, pool=gstep.graph.pool())
         except Exception as ex:          # capture unsupported in this configuration: run eagerly and say so
             import traceback
             traceback.print_exc(file=sys.stderr)
@@ -545,11 +546,6 @@ def main():
     clk = clocks.stop() if clocks else None
     if gstep is not None:
         launches = launches_per_graph * args.steps       # kernels replayed from the graph in the timed region
-    # per-GEMM CUDA-event timing needs eager launches (events cannot bracket nodes of a replayed graph)
-    esteps = max(2, min(args.steps, 10))
-    for i in range(2):
-        step_eager(i)
-    ms_eager, _, prof = timed(step_eager, esteps, profile=True)
     for i in range(3):
         step_e2e(i)
     e2e_collect()
@@ -599,6 +595,19 @@ def main():
     parity = None
     if not args.no_parity_check and world == 1 and args.precision == "bf16":      # single-process check (it builds a replica and steps it without collectives)
         parity = parity_check(cfg, wl, gstep, dev_batches[0], device)
+
+    # the captured graphs hold their own pool of saved activations (86 GB at the stress shape): release it before the eager
+    # passes below, which need the same amount again
+    gstep_was = gstep is not None
+    gstep = gstep_noopt = None
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    # per-GEMM CUDA-event timing needs eager launches (events cannot bracket nodes of a replayed graph)
+    esteps = max(2, min(args.steps, 10))
+    for i in range(2):
+        step_eager(i)
+    ms_eager, _, prof = timed(step_eager, esteps, profile=True)
 
     if rank == 0:
         pk = peaks()
@@ -692,7 +701,7 @@ def main():
             "fwd_bwd_allreduce_only": None if ms_noopt is None else {
                 "value": world * B * args.steps / (ms_noopt / 1e3), "unit": "samples/s", "ms_per_step": ms_noopt / args.steps},
             "allreduce_buckets_per_step": wl.red.launched, "allreduce_trace": comm, "host_enqueue_ms_per_step": host_ms,
-            "cuda_graph": gstep is not None, "cuda_graph_error": graph_err, "eager_ms_per_step": ms_eager / esteps,
+            "cuda_graph": gstep_was, "cuda_graph_error": graph_err, "eager_ms_per_step": ms_eager / esteps,
         }
         if args.batch:
             out["config"]["batch_override"] = args.batch

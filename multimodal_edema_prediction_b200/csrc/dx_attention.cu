@@ -13,6 +13,15 @@
 
 // bf16 tensor-core path for short self-attention (dx_attention_mma.cu)
 bool dx_attn_mma_supported(const void* const* ptrs, const long long* bs, const long long* rs, int n, int Sq, int Sk, int dh);
+bool dx_attn_mmat_supported(const void* const* ptrs, const long long* bs, const long long* rs, int n, int Sq, int Sk, int dh);
+int dx_attn_mmat_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
+                     long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse, int B, int H, int Sq,
+                     int Sk, int dh, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st);
+int dx_attn_mmat_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
+                     long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs, const void* go, long long go_bs,
+                     long long go_rs, void* dq, long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs,
+                     void* dv, long long dv_bs, long long dv_rs, const float* lse, float* Dws, int B, int H, int Sq, int Sk, int dh,
+                     DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st);
 int dx_attn_mma_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
                     long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse, int B, int H, int Sq,
                     int Sk, int dh, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st);
@@ -357,6 +366,9 @@ int dx_attn_fwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_
     const long long bs[4] = {q_bs, k_bs, v_bs, o_bs}, rs[4] = {q_rs, k_rs, v_rs, o_rs};
     if (dx_attn_mma_supported(ptrs, bs, rs, 4, Sq, Sk, dh))
       return dx_attn_mma_fwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, B, H, Sq, Sk, dh, drop, seed_dev, st);
+    // long sequences / dh = 128 (stress shape): tiled tensor-core kernels; few queries (perceiver latents) stay on the SIMT path
+    if (Sq >= 16 && lse && dx_attn_mmat_supported(ptrs, bs, rs, 4, Sq, Sk, dh))
+      return dx_attn_mmat_fwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, B, H, Sq, Sk, dh, drop, seed_dev, st);
   }
   AttnView Q{q, q_bs, q_rs}, K{k, k_bs, k_rs}, V{v, v_bs, v_rs};
   AttnViewW O{o, o_bs, o_rs};
@@ -383,6 +395,9 @@ int dx_attn_bwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_
     if (dx_attn_mma_supported(ptrs, bs, rs, 8, Sq, Sk, dh))
       return dx_attn_mma_bwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, go, go_bs, go_rs, dq, dq_bs, dq_rs, dk,
                              dk_bs, dk_rs, dv, dv_bs, dv_rs, lse, B, H, Sq, Sk, dh, drop, seed_dev, st);
+    if (Sq >= 16 && dx_attn_mmat_supported(ptrs, bs, rs, 8, Sq, Sk, dh))
+      return dx_attn_mmat_bwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, go, go_bs, go_rs, dq, dq_bs, dq_rs, dk,
+                              dk_bs, dk_rs, dv, dv_bs, dv_rs, lse, D_ws, B, H, Sq, Sk, dh, drop, seed_dev, st);
   }
   AttnView Q{q, q_bs, q_rs}, K{k, k_bs, k_rs}, V{v, v_bs, v_rs}, O{o, o_bs, o_rs}, GO{go, go_bs, go_rs};
   AttnViewW DQ{dq, dq_bs, dq_rs}, DK{dk, dk_bs, dk_rs}, DV{dv, dv_bs, dv_rs};

@@ -309,6 +309,313 @@ __global__ void __launch_bounds__(288) attn_mma_bwd_kernel(View q, View k, View 
   }
 }
 
+// =========================================================================================================================
+// Tiled variants: any sequence length and head dims up to 128 (the stress shape of BASELINE.json configs[4]: S = 513 / 129,
+// dh = 128, where the one-CTA-per-(sample, head) kernels above do not fit in shared memory and the SIMT fallback took 31 % of
+// the step).  Same warp-level mma.sync.m16n8k16 fragments and helpers; a CTA owns a 128-row tile of queries (forward, dQ) or
+// of keys (dK, dV) and streams the other operand through shared memory in 64-row tiles.  A fragments are re-read from shared
+// memory with ldmatrix inside the loops (keeping Q/dO/K/V fragments AND two 16 x 128 accumulators in registers would spill).
+// The backward is two launches (FlashAttention-2 style): the dQ kernel also produces D = <dO, o> for the dK/dV kernel.
+// =========================================================================================================================
+constexpr int TQ = 128;   // resident rows per CTA (8 warps x 16)
+constexpr int TS = 64;    // streamed rows per step
+
+// rows [r0, r0 + nrows) of a head slice -> shared rows [0, nrows), zero-filled past S
+template <int DH>
+__device__ __forceinline__ void load_rows_off(bf16* sm, const View& v, int b, int h, int r0, int nrows, int S) {
+  constexpr int CPR = DH / 8;
+  const bf16* base = v.p + (long long)b * v.bs + (long long)h * DH;
+  for (int idx = threadIdx.x; idx < nrows * CPR; idx += blockDim.x) {
+    const int r = idx / CPR, c = idx - r * CPR;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (r0 + r < S) u = *reinterpret_cast<const uint4*>(base + (long long)(r0 + r) * v.rs + c * 8);
+    *reinterpret_cast<uint4*>(sm + r * (DH + PAD) + c * 8) = u;
+  }
+}
+
+// c[2][4] (16 x 16) = A[m0..m0+16, :] . X[n0..n0+16, :]^T, both row-major [row][k] in shared memory (A fragments loaded per step)
+template <int DH>
+__device__ __forceinline__ void mma_xa_xt(float (&c)[2][4], uint32_t abase, int m0, uint32_t xbase, int n0, int lane) {
+  const int arow = m0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+  const int xrow = n0 + (lane & 7) + (lane >> 4) * 8;
+  const int xcol = ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int kk = 0; kk < DH / 16; ++kk) {
+    uint32_t a[4], r[4];
+    ldsm_x4(abase + (uint32_t)((arow * (DH + PAD) + kk * 16 + (lane >> 4) * 8) * 2), a);
+    ldsm_x4(xbase + (uint32_t)((xrow * (DH + PAD) + kk * 16 + xcol) * 2), r);
+    mma16816(c[0], a, r[0], r[1]);
+    mma16816(c[1], a, r[2], r[3]);
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(256) attn_mmat_fwd_kernel(View q, View k, View v, ViewW o, float* __restrict__ lse, int H, int Sq,
+                                                           int Sk, float scale, DxDrop drop,
+                                                           const unsigned long long* __restrict__ seed_dev) {
+  drop = dx_drop_resolve(drop, seed_dev);
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sK = sQ + TQ * (DH + PAD);
+  bf16* sV = sK + TS * (DH + PAD);
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int q0 = blockIdx.y * TQ;
+  load_rows_off<DH>(sQ, q, b, h, q0, TQ, Sq);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = lane & 3;
+  const int m0 = warp * 16;                          // local row of this warp inside the tile
+  const uint32_t uQ = smem_u32(sQ), uK = smem_u32(sK), uV = smem_u32(sV);
+  float acc[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  float mx[2] = {-INFINITY, -INFINITY}, ls[2] = {0.f, 0.f};
+  const float sc2 = scale * LOG2E;
+  const unsigned long long dbase = (unsigned long long)blockIdx.x * Sq;   // (b*H + h) * Sq
+  for (int kt = 0; kt < Sk; kt += TS) {
+    __syncthreads();                                  // the previous tile is no longer read
+    load_rows_off<DH>(sK, k, b, h, kt, TS, Sk);
+    load_rows_off<DH>(sV, v, b, h, kt, TS, Sk);
+    __syncthreads();
+#pragma unroll 1
+    for (int k0 = 0; k0 < TS; k0 += 16) {
+      if (kt + k0 >= Sk) break;                       // uniform per CTA
+      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      mma_xa_xt<DH>(s, uQ, m0, uK, k0, lane);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kt + k0 + nt * 8 + 2 * t + (e & 1);
+          s[nt][e] = key < Sk ? s[nt][e] * sc2 : -INFINITY;
+        }
+      uint32_t pa[4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float m = fmaxf(fmaxf(s[0][2 * r], s[0][2 * r + 1]), fmaxf(s[1][2 * r], s[1][2 * r + 1]));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        const float mnew = fmaxf(mx[r], m);           // finite: the first key block always holds a valid key
+        const float corr = ex2(mx[r] - mnew);
+        mx[r] = mnew;
+        float p00 = ex2(s[0][2 * r] - mnew), p01 = ex2(s[0][2 * r + 1] - mnew);
+        float p10 = ex2(s[1][2 * r] - mnew), p11 = ex2(s[1][2 * r + 1] - mnew);
+        ls[r] = ls[r] * corr + (p00 + p01) + (p10 + p11);
+        if (drop.thresh) {
+          const unsigned long long di =
+              (dbase + (unsigned)(q0 + m0 + (lane >> 2) + 8 * r)) * (unsigned long long)Sk + (unsigned)(kt + k0 + 2 * t);
+          p00 *= dx_drop_factor(drop, di);
+          p01 *= dx_drop_factor(drop, di + 1);
+          p10 *= dx_drop_factor(drop, di + 8);
+          p11 *= dx_drop_factor(drop, di + 9);
+        }
+#pragma unroll
+        for (int i = 0; i < DH / 8; ++i) {
+          acc[i][2 * r] *= corr;
+          acc[i][2 * r + 1] *= corr;
+        }
+        pa[r] = pack2(p00, p01);
+        pa[2 + r] = pack2(p10, p11);
+      }
+      mma_p_x<DH>(acc, pa, uV, k0, lane);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    ls[r] += __shfl_xor_sync(0xffffffffu, ls[r], 1);
+    ls[r] += __shfl_xor_sync(0xffffffffu, ls[r], 2);
+  }
+  store_frag<DH>(o, b, h, q0 + m0, Sq, lane, acc, 1.f / ls[0], 1.f / ls[1]);
+  if (lse && t == 0) {
+    const int g = lane >> 2;
+    float* lp = lse + ((long long)b * H + h) * Sq;
+    if (q0 + m0 + g < Sq) lp[q0 + m0 + g] = (mx[0] + log2f(ls[0])) * LN2;
+    if (q0 + m0 + g + 8 < Sq) lp[q0 + m0 + g + 8] = (mx[1] + log2f(ls[1])) * LN2;
+  }
+}
+
+// dQ for a 128-row query tile; also writes D[b,h,row] = <dO[row], o[row]> for the dK/dV kernel
+template <int DH>
+__global__ void __launch_bounds__(256) attn_mmat_bwd_dq_kernel(View q, View k, View v, View o, View go, ViewW dq,
+                                                              const float* __restrict__ lse, float* __restrict__ Dws, int H, int Sq,
+                                                              int Sk, float scale, DxDrop drop,
+                                                              const unsigned long long* __restrict__ seed_dev) {
+  drop = dx_drop_resolve(drop, seed_dev);
+  const unsigned long long dbase = (unsigned long long)blockIdx.x * Sq;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sG = sQ + TQ * (DH + PAD);
+  bf16* sK = sG + TQ * (DH + PAD);
+  bf16* sV = sK + TS * (DH + PAD);
+  float* sL = reinterpret_cast<float*>(sV + TS * (DH + PAD));
+  float* sD = sL + TQ;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int q0 = blockIdx.y * TQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  load_rows_off<DH>(sQ, q, b, h, q0, TQ, Sq);
+  load_rows_off<DH>(sG, go, b, h, q0, TQ, Sq);
+  for (int i = threadIdx.x; i < TQ; i += blockDim.x) sL[i] = q0 + i < Sq ? lse[((long long)b * H + h) * Sq + q0 + i] * LOG2E : 0.f;
+  __syncthreads();
+  for (int r = warp; r < TQ; r += 8) {               // D: one warp per query row, dO from shared memory, o from global
+    float d = 0.f;
+    if (q0 + r < Sq) {
+      const bf16* op = o.p + (long long)b * o.bs + (long long)(q0 + r) * o.rs + (long long)h * DH;
+      for (int c = 2 * lane; c < DH; c += 64) {
+        const float2 ov = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(op + c));
+        const float2 gv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sG + r * (DH + PAD) + c));
+        d = fmaf(ov.x, gv.x, fmaf(ov.y, gv.y, d));
+      }
+    }
+    d = dx_warp_sum(d);
+    if (lane == 0) {
+      sD[r] = d;
+      if (q0 + r < Sq) Dws[((long long)b * H + h) * Sq + q0 + r] = d;
+    }
+  }
+  __syncthreads();
+  const uint32_t uQ = smem_u32(sQ), uG = smem_u32(sG), uK = smem_u32(sK), uV = smem_u32(sV);
+  const float sc2 = scale * LOG2E;
+  const int m0 = warp * 16;
+  const float L[2] = {sL[m0 + g], sL[m0 + g + 8]}, Dr[2] = {sD[m0 + g], sD[m0 + g + 8]};
+  float acc[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int kt = 0; kt < Sk; kt += TS) {
+    __syncthreads();
+    load_rows_off<DH>(sK, k, b, h, kt, TS, Sk);
+    load_rows_off<DH>(sV, v, b, h, kt, TS, Sk);
+    __syncthreads();
+#pragma unroll 1
+    for (int k0 = 0; k0 < TS; k0 += 16) {
+      if (kt + k0 >= Sk) break;
+      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      mma_xa_xt<DH>(s, uQ, m0, uK, k0, lane);
+      mma_xa_xt<DH>(dp, uG, m0, uV, k0, lane);
+      float ds[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kt + k0 + nt * 8 + 2 * t + (e & 1);
+          const float p = key < Sk ? ex2(s[nt][e] * sc2 - L[e >> 1]) : 0.f;
+          float dpe = dp[nt][e];
+          if (drop.thresh)
+            dpe *= dx_drop_factor(drop, (dbase + (unsigned)(q0 + m0 + g + 8 * (e >> 1))) * (unsigned long long)Sk + (unsigned)key);
+          ds[nt][e] = p * (dpe - Dr[e >> 1]);
+        }
+      const uint32_t dsa[4] = {pack2(ds[0][0], ds[0][1]), pack2(ds[0][2], ds[0][3]), pack2(ds[1][0], ds[1][1]),
+                               pack2(ds[1][2], ds[1][3])};
+      mma_p_x<DH>(acc, dsa, uK, k0, lane);
+    }
+  }
+  store_frag<DH>(dq, b, h, q0 + m0, Sq, lane, acc, scale, scale);
+}
+
+// dK, dV for a 128-row key tile; queries (Q, dO, lse, D) streamed in 64-row tiles
+template <int DH>
+__global__ void __launch_bounds__(256) attn_mmat_bwd_kv_kernel(View q, View k, View v, View go, ViewW dk, ViewW dv,
+                                                              const float* __restrict__ lse, const float* __restrict__ Dws, int H,
+                                                              int Sq, int Sk, float scale, DxDrop drop,
+                                                              const unsigned long long* __restrict__ seed_dev) {
+  drop = dx_drop_resolve(drop, seed_dev);
+  const unsigned long long dbase = (unsigned long long)blockIdx.x * Sq;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sK = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sV = sK + TQ * (DH + PAD);
+  bf16* sQ = sV + TQ * (DH + PAD);
+  bf16* sG = sQ + TS * (DH + PAD);
+  float* sL = reinterpret_cast<float*>(sG + TS * (DH + PAD));
+  float* sD = sL + TS;
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int kbase = blockIdx.y * TQ;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  load_rows_off<DH>(sK, k, b, h, kbase, TQ, Sk);
+  load_rows_off<DH>(sV, v, b, h, kbase, TQ, Sk);
+  const uint32_t uQ = smem_u32(sQ), uG = smem_u32(sG), uK = smem_u32(sK), uV = smem_u32(sV);
+  const float sc2 = scale * LOG2E;
+  const int m0 = warp * 16;                          // local key row of this warp
+  float ak[DH / 8][4], av[DH / 8][4];
+#pragma unroll
+  for (int i = 0; i < DH / 8; ++i) {
+    ak[i][0] = ak[i][1] = ak[i][2] = ak[i][3] = 0.f;
+    av[i][0] = av[i][1] = av[i][2] = av[i][3] = 0.f;
+  }
+  for (int qt = 0; qt < Sq; qt += TS) {
+    __syncthreads();
+    load_rows_off<DH>(sQ, q, b, h, qt, TS, Sq);
+    load_rows_off<DH>(sG, go, b, h, qt, TS, Sq);
+    for (int i = threadIdx.x; i < TS; i += blockDim.x) {
+      const bool ok = qt + i < Sq;
+      sL[i] = ok ? lse[((long long)b * H + h) * Sq + qt + i] * LOG2E : 0.f;
+      sD[i] = ok ? Dws[((long long)b * H + h) * Sq + qt + i] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int qq = 0; qq < TS; qq += 16) {
+      if (qt + qq >= Sq) break;
+      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      mma_xa_xt<DH>(s, uK, m0, uQ, qq, lane);      // S^T block: rows = keys, columns = queries
+      mma_xa_xt<DH>(dp, uV, m0, uG, qq, lane);     // dP^T block
+      float p[2][4], ds[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int ql = qq + nt * 8 + 2 * t + (e & 1);      // local query index in the streamed tile
+          const int qi = qt + ql;
+          const float pe = qi < Sq ? ex2(s[nt][e] * sc2 - sL[ql]) : 0.f;
+          const float mk = drop.thresh ? dx_drop_factor(drop, (dbase + (unsigned)qi) * (unsigned long long)Sk +
+                                                                  (unsigned)(kbase + m0 + g + 8 * (e >> 1)))
+                                       : 1.f;
+          ds[nt][e] = pe * (dp[nt][e] * mk - sD[ql]);
+          p[nt][e] = pe * mk;
+        }
+      const uint32_t pa[4] = {pack2(p[0][0], p[0][1]), pack2(p[0][2], p[0][3]), pack2(p[1][0], p[1][1]), pack2(p[1][2], p[1][3])};
+      const uint32_t dsa[4] = {pack2(ds[0][0], ds[0][1]), pack2(ds[0][2], ds[0][3]), pack2(ds[1][0], ds[1][1]),
+                               pack2(ds[1][2], ds[1][3])};
+      mma_p_x<DH>(av, pa, uG, qq, lane);     // dV += P^T dO
+      mma_p_x<DH>(ak, dsa, uQ, qq, lane);    // dK += dS^T Q
+    }
+  }
+  store_frag<DH>(dk, b, h, kbase + m0, Sk, lane, ak, scale, scale);
+  store_frag<DH>(dv, b, h, kbase + m0, Sk, lane, av, 1.f, 1.f);
+}
+
+template <int DH>
+int launch_fwd_tiled(const View& q, const View& k, const View& v, const ViewW& o, float* lse, int B, int H, int Sq, int Sk,
+                     float scale, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st) {
+  const size_t smem = (size_t)(TQ + 2 * TS) * (DH + PAD) * 2;
+  auto kern = attn_mmat_fwd_kernel<DH>;
+  static bool attr = false;
+  if (!attr) {
+    DX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid(B * H, (Sq + TQ - 1) / TQ);
+  kern<<<grid, 256, smem, st>>>(q, k, v, o, lse, H, Sq, Sk, scale, drop, seed_dev);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
+template <int DH>
+int launch_bwd_tiled(const View& q, const View& k, const View& v, const View& o, const View& go, const ViewW& dq, const ViewW& dk,
+                     const ViewW& dv, const float* lse, float* Dws, int B, int H, int Sq, int Sk, float scale, DxDrop drop,
+                     const unsigned long long* seed_dev, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * TQ + 2 * TS) * (DH + PAD) * 2 + 2 * TQ * sizeof(float);
+  auto kq = attn_mmat_bwd_dq_kernel<DH>;
+  auto kkv = attn_mmat_bwd_kv_kernel<DH>;
+  static bool attr = false;
+  if (!attr) {
+    DX_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DX_CUDA(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 gq(B * H, (Sq + TQ - 1) / TQ), gk(B * H, (Sk + TQ - 1) / TQ);
+  kq<<<gq, 256, smem, st>>>(q, k, v, o, go, dq, lse, Dws, H, Sq, Sk, scale, drop, seed_dev);
+  DX_LAUNCH_CHECK();
+  kkv<<<gk, 256, smem, st>>>(q, k, v, go, dk, dv, lse, Dws, H, Sq, Sk, scale, drop, seed_dev);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
+}
+
 inline bool view_ok(const void* p, long long bs, long long rs, int dh) {
   return ((uintptr_t)p % 16 == 0) && (bs % 8 == 0) && (rs % 8 == 0) && (dh % 8 == 0);
 }
@@ -358,6 +665,40 @@ bool dx_attn_mma_supported(const void* const* ptrs, const long long* bs, const l
   for (int i = 0; i < n; ++i)
     if (!dx_attn_mma::view_ok(ptrs[i], bs[i], rs[i], dh)) return false;
   return true;
+}
+
+// tiled kernels: dh 64 / 128, any sequence length
+bool dx_attn_mmat_supported(const void* const* ptrs, const long long* bs, const long long* rs, int n, int Sq, int Sk, int dh) {
+  if (!(dh == 64 || dh == 128)) return false;
+  if (Sq < 1 || Sk < 1) return false;
+  for (int i = 0; i < n; ++i)
+    if (!dx_attn_mma::view_ok(ptrs[i], bs[i], rs[i], dh)) return false;
+  return true;
+}
+
+int dx_attn_mmat_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
+                     long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse, int B, int H, int Sq,
+                     int Sk, int dh, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st) {
+  using namespace dx_attn_mma;
+  View Q{(const bf16*)q, q_bs, q_rs}, K{(const bf16*)k, k_bs, k_rs}, V{(const bf16*)v, v_bs, v_rs};
+  ViewW O{(bf16*)o, o_bs, o_rs};
+  const float scale = 1.f / sqrtf((float)dh);
+  if (dh == 64) return launch_fwd_tiled<64>(Q, K, V, O, lse, B, H, Sq, Sk, scale, drop, seed_dev, st);
+  return launch_fwd_tiled<128>(Q, K, V, O, lse, B, H, Sq, Sk, scale, drop, seed_dev, st);
+}
+
+int dx_attn_mmat_bwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
+                     long long v_bs, long long v_rs, const void* o, long long o_bs, long long o_rs, const void* go, long long go_bs,
+                     long long go_rs, void* dq, long long dq_bs, long long dq_rs, void* dk, long long dk_bs, long long dk_rs,
+                     void* dv, long long dv_bs, long long dv_rs, const float* lse, float* Dws, int B, int H, int Sq, int Sk, int dh,
+                     DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st) {
+  using namespace dx_attn_mma;
+  View Q{(const bf16*)q, q_bs, q_rs}, K{(const bf16*)k, k_bs, k_rs}, V{(const bf16*)v, v_bs, v_rs}, O{(const bf16*)o, o_bs, o_rs},
+      GO{(const bf16*)go, go_bs, go_rs};
+  ViewW DQ{(bf16*)dq, dq_bs, dq_rs}, DK{(bf16*)dk, dk_bs, dk_rs}, DV{(bf16*)dv, dv_bs, dv_rs};
+  const float scale = 1.f / sqrtf((float)dh);
+  if (dh == 64) return launch_bwd_tiled<64>(Q, K, V, O, GO, DQ, DK, DV, lse, Dws, B, H, Sq, Sk, scale, drop, seed_dev, st);
+  return launch_bwd_tiled<128>(Q, K, V, O, GO, DQ, DK, DV, lse, Dws, B, H, Sq, Sk, scale, drop, seed_dev, st);
 }
 
 int dx_attn_mma_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,

@@ -21,8 +21,9 @@ class CudaGraphStep:
         # Warm-up on the CURRENT stream (lazy allocations, cudaFuncSetAttribute).  The usual side-stream warm-up makes the
         # autograd engine record cross-stream dependencies on the flat gradient buffer, which a later capture rejects
         # ("dependency created on uncaptured work in another stream").
-        for _ in range(warmup):
-            out = fn()
+        out = None
+        for _ in range(warmup):          # warmup=0: a second graph of an already warmed-up step (shares `pool`, no eager copy of
+            out = fn()                   # the activations next to the first graph's pool)
         del out                          # no eager autograd graph may be released in the middle of the capture
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()

@@ -155,7 +155,8 @@ def test_relayout_fwd_bwd(ops, dt):
 
 
 @pytest.mark.parametrize("dt", DT)
-@pytest.mark.parametrize("S,D,H", [(129, 128, 2), (33, 64, 2), (5, 8, 2), (35, 24, 2), (70, 256, 2)])
+@pytest.mark.parametrize("S,D,H", [(129, 128, 2), (33, 64, 2), (5, 8, 2), (35, 24, 2), (70, 256, 2),
+                                   (513, 256, 2), (129, 256, 2), (200, 128, 2), (300, 512, 4)])     # tiled kernels: dh 128 / S > 144
 def test_attention_fwd_bwd(ops, dt, S, D, H):
     B = 3
     qkv = rnd(B, S, 3 * D, dtype=dt, seed=30, scale=0.7)
@@ -441,7 +442,7 @@ def test_dropout_matches_generator_spec(ops, dt):
 
 
 @pytest.mark.parametrize("dt", DT)
-@pytest.mark.parametrize("S,D,H", [(129, 128, 2), (33, 64, 2), (35, 24, 2)])
+@pytest.mark.parametrize("S,D,H", [(129, 128, 2), (33, 64, 2), (35, 24, 2), (513, 256, 2), (150, 128, 2)])
 def test_attention_dropout_fwd_bwd(ops, dt, S, D, H):
     """Attention-probability dropout in the tensor-core (bf16, dh 32/64) and SIMT kernels against the emulator running on
     the same generator; the backward regenerates the mask."""
