@@ -77,6 +77,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// TMA prefetch of one box into L2 (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -235,10 +240,18 @@ struct TcParams {
   int splits, kb_per_split;              // split-K (dW GEMMs with few output tiles): partial sums are red.add'ed into out
   int epi_mask;                          // staged epilogue: compile-time feature mask (dx_epi_mask), -1 = runtime flags
   int raster_m;                          // 1: consecutive work units walk M first (few M tiles sharing a large B column block)
+  int chunked;                           // 1: every worker owns a contiguous run of work units (unit_range)
+  int l2pf;                              // experiment (default 0 = off): every l2pf k-blocks the producer prefetches the NEXT l2pf boxes of its
+                                         // K-major A rows into L2 in one burst (cp.async.bulk.prefetch.tensor)
   int fault;                             // test hook (DX_GEMM_FAULT): bit 0 = from a CTA's third tile on the accumulator is NOT reset, i.e. a
                                          // TMEM slot-reuse bug (tests/test_gemm_production_gpu.py proves its checks catch it); bits 1 / 2 =
                                          // the staged epilogue skips its side-tensor loads / its stores (timing experiments, wrong results)
 };
+
+// Work units of one persistent worker (CTA or CTA pair): strided (unit = w, w + W, ...: neighbouring workers run neighbouring
+// tiles at the same time) or chunked (a contiguous run per worker: with N running fastest one worker walks all N tiles of an
+// M block, so only its first pass over the A block comes from DRAM).
+__device__ __forceinline__ void unit_range(const TcParams& p, int w, int W, int& first, int& end, int& step);
 
 // work unit -> tile indices.  The fast-running index is the one whose tiles share the LARGER operand block, so that block
 // is fetched from DRAM once and hit in L2 by the neighbouring tiles (ncu: 2.1x the algorithmic DRAM bytes for the
@@ -253,6 +266,19 @@ __device__ __forceinline__ void tile_decode(const TcParams& p, int tile, int& mi
   } else {
     mi = r / p.tiles_n;
     ni = r - mi * p.tiles_n;
+  }
+}
+
+__device__ __forceinline__ void unit_range(const TcParams& p, int w, int W, int& first, int& end, int& step) {
+  if (p.chunked) {
+    const int base = p.total_tiles / W, rem = p.total_tiles - base * W;
+    first = w * base + (w < rem ? w : rem);
+    end = first + base + (w < rem ? 1 : 0);
+    step = 1;
+  } else {
+    first = w;
+    end = p.total_tiles;
+    step = W;
   }
 }
 
@@ -402,10 +428,12 @@ __device__ __forceinline__ void staged_epilogue(const DxEpi& e0, const TcParams&
   int mi = 0, ni = 0, z = 0;
   DxRowRaw raw_next{1.f, 1.f, 0.f, 1.f};
   bool raw_ok = false;
-  if ((int)blockIdx.x / CL < p.total_tiles) tile_decode(p, (int)blockIdx.x / CL, mi, ni, z);
-  for (int unit = (int)blockIdx.x / CL; unit < p.total_tiles; unit += ustep, ++tcount) {
+  int ufirst, uend, ustride;
+  unit_range(p, (int)blockIdx.x / CL, ustep, ufirst, uend, ustride);
+  if (ufirst < uend) tile_decode(p, ufirst, mi, ni, z);
+  for (int unit = ufirst; unit < uend; unit += ustride, ++tcount) {
     int mi2 = 0, ni2 = 0, z2 = -1;
-    if (unit + ustep < p.total_tiles) tile_decode(p, unit + ustep, mi2, ni2, z2);
+    if (unit + ustride < uend) tile_decode(p, unit + ustride, mi2, ni2, z2);
     const int n0 = ni * BN;
     const int m0 = mi * (BM * CL) + m_off;
     const uint32_t slot = tcount & 1, use = tcount >> 1;
@@ -614,7 +642,8 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + BKE - 1) / BKE;
   const uint32_t cta_rank = CL == 2 ? cluster_ctarank() : 0;
-  const int unit0 = (int)blockIdx.x / CL, ustep = (int)gridDim.x / CL;
+  int unit0, uend, ustep;
+  unit_range(p, (int)blockIdx.x / CL, (int)gridDim.x / CL, unit0, uend, ustep);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -655,7 +684,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
       // ===== TMA producer =====
       uint32_t it = 0;   // running k-block counter across tiles
       const uint32_t leader_full = PAIR ? mapa_u32(smem_u32(full_bar), 0) : 0;
-      for (int unit = unit0; unit < p.total_tiles; unit += ustep) {
+      for (int unit = unit0; unit < uend; unit += ustep) {
         const int tile = unit / p.splits, split = unit - tile * p.splits;
         int mi, ni, z;
         tile_decode(p, tile, mi, ni, z);
@@ -669,6 +698,12 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
           uint8_t* sa = smem + s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           const int k0 = kb * BKE;
+          if (!A_MN && p.l2pf > 0 && (kb - kb_lo) % p.l2pf == 0) {
+            for (int j = 0; j < p.l2pf; ++j) {
+              const int kk = kb + p.l2pf + j;
+              if (kk < kb_hi) tma_prefetch_l2_3d(&tmA, kk * BKE, m0, z);
+            }
+          }
           if (MC) {
             // own A tile locally; own half of the B block into BOTH CTAs (the other half arrives from the peer)
             mbar_arrive_expect_tx(full_bar + s, STAGE_BYTES);
@@ -730,7 +765,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
       constexpr uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((A_MN ? 1u : 0u) << 15) |
                                  ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * (PAIR ? 2 : 1)) >> 4) << 24);
       uint32_t it = 0, tcount = 0;
-      for (int unit = unit0; unit < p.total_tiles; unit += ustep, ++tcount) {
+      for (int unit = unit0; unit < uend; unit += ustep, ++tcount) {
         const int split = unit % p.splits;
         const int kb_lo = split * p.kb_per_split, kb_hi = min(num_kb, kb_lo + p.kb_per_split);
         const uint32_t slot = tcount & 1, use = tcount >> 1;
@@ -795,7 +830,7 @@ __global__ void __launch_bounds__(NTHREADS) dx_gemm_tc_kernel(const __grid_const
     } else {
       uint32_t tcount = 0;
       const uint32_t empty_remote = CTAS == 2 ? mapa_u32(smem_u32(tmem_empty_bar), 0) : 0;
-      for (int unit = unit0; unit < p.total_tiles; unit += ustep, ++tcount) {
+      for (int unit = unit0; unit < uend; unit += ustep, ++tcount) {
         const int tile = unit / p.splits;
         int mi, ni, z;
         tile_decode(p, tile, mi, ni, z);
@@ -877,6 +912,12 @@ int launch_cfg(const dx_gemm_desc* d, const CUtensorMap& ta, const CUtensorMap& 
   if (const char* env = getenv("DX_GEMM_RASTER_M")) pp.raster_m = atoi(env) != 0;
   pp.fault = 0;
   if (const char* env = getenv("DX_GEMM_FAULT")) pp.fault = atoi(env);   // bit 0: injected bug; bits 1, 2: skip the side loads / the stores
+  // measured on B200 (profiles/r02_gemm_exp_l2pf.json): prefetching 2..16 boxes ahead makes the deep-K GEMMs 10-30 % SLOWER
+  // (the prefetches compete for the same per-SM TMA request capacity as the loads), so it is off; DX_GEMM_L2PF=n enables it
+  pp.l2pf = 0;
+  if (const char* env = getenv("DX_GEMM_L2PF")) pp.l2pf = atoi(env);
+  pp.chunked = 0;
+  if (const char* env = getenv("DX_GEMM_CHUNK")) pp.chunked = atoi(env) != 0;
   long long total = (long long)pp.tiles_n * pp.tiles_m * (d->batch > 1 ? d->batch : 1);
   static int dev_sms = 0;
   if (!dev_sms) {
