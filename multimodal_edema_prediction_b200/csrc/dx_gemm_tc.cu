@@ -156,6 +156,32 @@ int launch_staged(const dx_gemm_desc* d, int bn, int stages, int ctas, const CUt
 
 }  // namespace
 
+// Wave-quantisation fix for the CTA-pair GEMMs: the rows covered by whole waves of 256-row pair tiles run on the pair kernel,
+// the remaining rows as a second launch of 128-row single-CTA tiles (twice as many, half as long: 258 pair tiles on 74 pairs
+// = 3.49 -> 4 waves become 3 + ~0.55).  Only the M extent and the row-indexed pointers of the descriptor change.
+static thread_local int g_tail_depth = 0;      // > 0: inside a split launch (no further splitting)
+static thread_local int g_force_single = 0;    // the tail part: single-CTA tiles
+
+static dx_gemm_desc rows_from(const dx_gemm_desc& d, int m1) {
+  dx_gemm_desc t = d;
+  const long long osz = d.out_dtype == DX_BF16 ? 2 : 4, asz = d.act_dtype == DX_BF16 ? 2 : 4;
+  auto adv = [](const void* p, long long bytes) -> void* { return p ? (void*)((const char*)p + bytes) : nullptr; };
+  t.M = d.M - m1;
+  t.A = adv(d.A, (d.a_mn ? (long long)m1 : (long long)m1 * d.lda) * 2);
+  t.out = adv(d.out, (long long)m1 * d.ldo * osz);
+  t.out2 = adv(d.out2, (long long)m1 * d.ldo2 * asz);
+  t.res = adv(d.res, (long long)m1 * d.ldr * asz);
+  t.aux = adv(d.aux, (long long)m1 * d.ldx * asz);
+  t.cx = adv(d.cx, (long long)m1 * d.ldc * asz);
+  t.row_scale = (const float*)adv(d.row_scale, 4LL * m1);
+  t.row_scale2 = (const float*)adv(d.row_scale2, 4LL * m1);
+  t.coef_num = (const float*)adv(d.coef_num, 4LL * m1);
+  t.coef_den = (const float*)adv(d.coef_den, 4LL * m1);
+  t.row_sumsq = (float*)adv(d.row_sumsq, 4LL * m1);
+  t.row_dot = (float*)adv(d.row_dot, 4LL * m1);
+  return t;
+}
+
 int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int a_sbo, int b_lbo, int b_sbo,
                       cudaStream_t stream) {
   int rc = get_encode_fn();
@@ -223,7 +249,38 @@ int dx_gemm_tc_launch(const dx_gemm_desc* d, int bn, int stages, int a_lbo, int 
       const int budget = 232448 - 1536 - (staged ? NEPI * (nbufs * STG_BYTES + 512) : 0);
       const int stage_bytes = (BM + bn / 2) * BK * 2;
       const int st2 = 6 * stage_bytes <= budget ? 6 : ((bn == 256 && 4 * stage_bytes <= budget) ? 4 : 0);
-      if (st2) { ctas = 2; stages = st2; }
+      if (st2 && !g_force_single) { ctas = 2; stages = st2; }
+    }
+  }
+  if (ctas == 2 && g_tail_depth == 0) {
+    // Measured on B200 (profiles/r02_gemm_exp_tailsplit.json): NOT a win — a 128-row single-CTA tile stages 48 KB per k-block
+    // against the pair's 32 KB per SM, and these GEMMs are bound by the per-SM operand ingest, so the "half-height" tail
+    // tiles take ~0.8x (not 0.5x) of a pair tile: FFN-in 142 -> 161 us, dW 137 -> 181 us.  Off unless DX_GEMM_TAILSPLIT=1.
+    static int dev_sms = 0;
+    const char* ts_env = getenv("DX_GEMM_TAILSPLIT");
+    const int tail_split = ts_env ? (atoi(ts_env) != 0) : 0;
+    if (!dev_sms) {
+      int dev = 0;
+      DX_CUDA(cudaGetDevice(&dev));
+      DX_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int sms = dev_sms - dx_gemm_reserved_sms() > 16 ? dev_sms - dx_gemm_reserved_sms() : dev_sms;
+    const int workers = sms / 2, tiles_n = dx_ceil_div(d->N, bn), tiles_m = dx_ceil_div(d->M, 2 * BM);
+    const int total = tiles_m * tiles_n, full = total / workers, rem = total - full * workers;
+    const int m1 = (full * workers / tiles_n) * 2 * BM;      // rows covered by whole waves (whole 256-row blocks only)
+    if (tail_split && full >= 1 && rem > 0 && rem * 10 <= workers * 8 && m1 > 0 && m1 < d->M &&
+        (long long)dx_ceil_div(d->M - m1, BM) * tiles_n <= sms) {
+      dx_gemm_desc head = *d, tail = rows_from(*d, m1);
+      head.M = m1;
+      ++g_tail_depth;
+      rc = dx_gemm_tc_launch(&head, 0, 0, a_lbo, a_sbo, b_lbo, b_sbo, stream);
+      if (!rc) {
+        g_force_single = 1;
+        rc = dx_gemm_tc_launch(&tail, 0, 0, a_lbo, a_sbo, b_lbo, b_sbo, stream);
+        g_force_single = 0;
+      }
+      --g_tail_depth;
+      return rc;
     }
   }
   // B-multicast cluster for the HBM-bound staged shapes (shallow K, many M tiles re-reading the same B block).  Measured
