@@ -655,11 +655,16 @@ def main():
         # the family mixes tensor-bound (deep K) and HBM-bound (K <= 512, N = dim) launches: per-launch speed of light
         # max(flops / bf16 peak, algorithmic bytes / copy bandwidth), summed, against the measured time
         ideal_ms = sum(sol(r[2], r[3]) for r in tc) * 1e3
-        traffic, traffic_src = None, None
+        traffic, traffic_src, step_dram = None, None, None
         try:      # DRAM bytes per launch of the same kernel family from the committed ncu capture of this command (c2 only)
             if cfg["key"] == "c2":
                 tj = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_dram_bytes.json")))
                 traffic = tj["dram_bytes_per_launch"]
+                # whole-step DRAM traffic of the same capture next to SURVEY 8(d)'s ideal-fusion figure (8.9 GB activations +
+                # 0.26 GB weights forward, x3 for training = 26.8 GB at B=256)
+                step_dram = {"measured_bytes_per_step": tj["step_dram_bytes"], "read": tj["step_dram_read_bytes"],
+                             "write": tj["step_dram_write_bytes"], "survey_ideal_bytes_per_step": 26.8e9,
+                             "ratio": tj["step_dram_bytes"] / 26.8e9, "source": "profiles/r02_launches_dram.csv (ncu, 2 eager steps)"}
                 traffic_src = "profiles/r02_gemm_dram_bytes.json (ncu dram__bytes_read+write, mean over the step's GEMM launches)"
         except Exception:
             pass
@@ -694,7 +699,7 @@ def main():
                            l2="working set >> 126 MB L2 (every residual-stream tensor alone exceeds it), distinct input batches cycled"),
             "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": wl.h2d_bytes(dev_batches[0]), "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "roofline": roof, "attn": attn_rec, "cpu_baseline": cpu, "cpu_baseline_c1": cpu_c1, "clocks": clk,
+            "gpu_launches": launches, "roofline": roof, "step_dram": step_dram, "attn": attn_rec, "cpu_baseline": cpu, "cpu_baseline_c1": cpu_c1, "clocks": clk,
             "parity_check": parity,
             "model_tflops": value * fl / 1e12,
             "model_frac_of_bf16_peak": value * fl / 1e12 / (world * pk["bf16_tflops_sustained"]),
