@@ -14,6 +14,11 @@
 // bf16 tensor-core path for short self-attention (dx_attention_mma.cu)
 bool dx_attn_mma_supported(const void* const* ptrs, const long long* bs, const long long* rs, int n, int Sq, int Sk, int dh);
 bool dx_attn_mmat_supported(const void* const* ptrs, const long long* bs, const long long* rs, int n, int Sq, int Sk, int dh);
+// tcgen05 / TMEM forward (dx_attention_tc.cu): dh = 64, Sk <= 256, Sq >= 64 — the event axis of the DuETT blocks
+bool dx_attn_tc_supported(const void* const* ptrs, const long long* bs, const long long* rs, int n, int Sq, int Sk, int dh);
+int dx_attn_tc_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
+                   long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse, int B, int H, int Sq,
+                   int Sk, int dh, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st);
 int dx_attn_mmat_fwd(const void* q, long long q_bs, long long q_rs, const void* k, long long k_bs, long long k_rs, const void* v,
                      long long v_bs, long long v_rs, void* o, long long o_bs, long long o_rs, float* lse, int B, int H, int Sq,
                      int Sk, int dh, DxDrop drop, const unsigned long long* seed_dev, cudaStream_t st);
@@ -364,6 +369,8 @@ int dx_attn_fwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_
   if (dtype == DX_BF16 && !attn_force_simt()) {
     const void* ptrs[4] = {q, k, v, o};
     const long long bs[4] = {q_bs, k_bs, v_bs, o_bs}, rs[4] = {q_rs, k_rs, v_rs, o_rs};
+    if (dx_attn_tc_supported(ptrs, bs, rs, 4, Sq, Sk, dh))
+      return dx_attn_tc_fwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, B, H, Sq, Sk, dh, drop, seed_dev, st);
     if (dx_attn_mma_supported(ptrs, bs, rs, 4, Sq, Sk, dh))
       return dx_attn_mma_fwd(q, q_bs, q_rs, k, k_bs, k_rs, v, v_bs, v_rs, o, o_bs, o_rs, lse, B, H, Sq, Sk, dh, drop, seed_dev, st);
     // long sequences / dh = 128 (stress shape): tiled tensor-core kernels; few queries (perceiver latents) stay on the SIMT path

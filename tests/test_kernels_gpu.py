@@ -172,6 +172,39 @@ def test_attention_fwd_bwd(ops, dt, S, D, H):
     assert rel(dqkv, torch.cat([rq, rk, rv], 2)) < TOL[dt]
 
 
+@pytest.mark.parametrize("B,Sq,Sk,D,H,p", [(3, 129, 129, 128, 2, 0.0), (1, 64, 64, 64, 1, 0.0), (2, 128, 128, 128, 2, 0.2),
+                                          (2, 144, 144, 192, 3, 0.0), (2, 256, 256, 128, 2, 0.1), (2, 130, 77, 128, 2, 0.0),
+                                          (2, 300, 17, 64, 1, 0.3), (5, 193, 193, 128, 2, 0.0), (2, 129, 129, 128, 2, 0.25),
+                                          (2, 257, 96, 64, 1, 0.1), (3, 129, 33, 128, 2, 0.0)])
+def test_attention_tcgen05_forward(ops, monkeypatch, B, Sq, Sk, D, H, p):
+    """tcgen05 / TMEM forward (dx_attention_tc.cu: dh = 64, Sk <= 256, Sq >= 64 — the event axis): against the emulator and
+    against the mma.sync kernel it replaces (DX_ATTN_TC=0) on the same dropout mask; tile edges (Sq = 128k, and 128k + 1 where
+    the last row runs on the CTA's CUDA-core warp), register-resident (Sk <= 160) and two-pass softmax, key counts that are not
+    multiples of 16 / 32 / 64, cross attention, a single batch row."""
+    bf = torch.bfloat16
+    drop = (p, 24680) if p else None
+    if Sq == Sk:
+        qkv = rnd(B, Sq, 3 * D, dtype=bf, seed=130, scale=0.7)          # packed projections, strided head views
+        q, k, v = qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:]
+    else:
+        q, k, v = rnd(B, Sq, D, dtype=bf, seed=131, scale=0.7), rnd(B, Sk, D, dtype=bf, seed=132, scale=0.7), rnd(B, Sk, D, dtype=bf, seed=133)
+    args = (q, k, v, H) + ((drop,) if drop else ())
+    o, lse = ops.attn_fwd(*args)
+    ro, rlse = E.attn_fwd(*cpu(q, k, v), H, *((drop,) if drop else ()))
+    assert rel(o, ro) < TOL[bf] * (2 if p else 1) and rel(lse, rlse) < 1e-3
+    monkeypatch.setenv("DX_ATTN_TC", "0")
+    o2, lse2 = ops.attn_fwd(*args)
+    monkeypatch.delenv("DX_ATTN_TC")
+    assert rel(o, o2) < TOL[bf] and rel(lse, lse2) < 1e-4
+    # the mma.sync backward consumes the tcgen05 forward's o / lse and regenerates the same mask
+    go = rnd(B, Sq, D, dtype=bf, seed=134)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ops.attn_bwd(q, k, v, o, go, lse, H, dq, dk, dv, *((drop,) if drop else ()))
+    rq, rk, rv = torch.empty(B, Sq, D), torch.empty(B, Sk, D), torch.empty(B, Sk, D)
+    E.attn_bwd(*cpu(q, k, v, o, go, lse), H, rq, rk, rv, *((drop,) if drop else ()))
+    assert rel(dq, rq) < TOL[bf] * 2 and rel(dk, rk) < TOL[bf] * 2 and rel(dv, rv) < TOL[bf] * 2
+
+
 def test_cross_attention_few_queries(ops):
     B, Sq, Sk, D, H = 2, 7, 200, 256, 4
     q, k, v = rnd(B, Sq, D, seed=33), rnd(B, Sk, D, seed=34), rnd(B, Sk, D, seed=35)
