@@ -149,6 +149,14 @@ int dx_attn_bwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_
                 int64_t dv_bs, int64_t dv_rs, const float* lse, float* D_ws, int B, int H, int Sq, int Sk, int dh,
                 int dtype, float drop_p, uint64_t drop_seed, const uint64_t* drop_seed_dev, void* stream);
 
+/* Head-averaged attention probabilities out[b,i,j] = 1/H sum_h exp(<q_bih, k_bjh>/sqrt(dh) - lse[b,h,i]), out [B,Sq,Sk] f32,
+ * from the q / k projections and the lse of a dropout-free dx_attn_fwd call (same addressing as dx_attn_fwd).
+ * Replaces: the attention-weights return of nn.MultiheadAttention(need_weights=True, average_attn_weights=True) in
+ * _PerceiverBlock.forward(return_attn=True) (models/main_architecture_duett.py:762,772), surfaced as img_attn / ts_attn by
+ * PatchDualPathologyPerceiver.forward (:621-631,651-653) and TeacherModel.forward (:1123-1128) for visualisation. */
+int dx_attn_probs_mean(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_rs, const float* lse,
+                       float* out, int B, int H, int Sq, int Sk, int dh, int dtype, void* stream);
+
 /* Value/count embedding into psi[B,T+1,V+1,d] (duett/duett.py:245-266 == models/main_architecture_duett.py:31-65, the
  * per-variable Python loop): count lookup (n_obs_embedding, clip 0..15), V grouped MLPs
  * Linear(2,64)-ReLU-BatchNorm(batch stats over B*T)-Linear(64,d), static column, [REP] row, MASK substitution.

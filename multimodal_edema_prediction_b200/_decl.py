@@ -14,6 +14,7 @@ SIGNATURES = {
     "dx_cast": [P, I, P, I, L, P],
     "dx_attn_fwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, I, I, I, I, I, I, F, U64, P, P],
     "dx_attn_bwd": [P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, L, L, P, P, I, I, I, I, I, I, F, U64, P, P],
+    "dx_attn_probs_mean": [P, L, L, P, L, L, P, P, I, I, I, I, I, I, P],
     "dx_dropout": [P, P, L, F, U64, P, I, P],
     "dx_rowdot_bias": [P, P, P, P, I, I, I, P],
     "dx_rowdot_scale": [P, P, P, P, I, I, I, P],

@@ -339,6 +339,31 @@ int launch_bwd(const AttnView& q, const AttnView& k, const AttnView& v, const At
   return DX_OK;
 }
 
+// Head-averaged attention probabilities, the second return value of nn.MultiheadAttention(need_weights=True,
+// average_attn_weights=True) in _PerceiverBlock.forward(return_attn=True) (models/main_architecture_duett.py:762,772):
+//   out[b,i,j] = 1/H * sum_h exp(scale * <q[b,i,h,:], k[b,j,h,:]> - lse[b,h,i])
+// with lse the row log-sum-exp dx_attn_fwd wrote.  Inference-time visualisation (7 pathology queries over 1369 patch or 24
+// hour tokens): one CTA per (query, 128 keys), the query row in shared memory, one key per thread.
+template <typename T>
+__global__ void __launch_bounds__(NTH) attn_probs_mean_kernel(AttnView Q, AttnView K, const float* __restrict__ lse,
+                                                             float* __restrict__ out, int H, int Sq, int Sk, int dh,
+                                                             float scale) {
+  extern __shared__ float sq[];   // H * dh
+  const int b = blockIdx.z, i = blockIdx.y;
+  for (int t = threadIdx.x; t < H * dh; t += NTH) sq[t] = ldv<T>(Q.p, (long long)b * Q.bs + (long long)i * Q.rs + t);
+  __syncthreads();
+  const int j = blockIdx.x * NTH + threadIdx.x;
+  if (j >= Sk) return;
+  const long long koff = (long long)b * K.bs + (long long)j * K.rs;
+  float acc = 0.f;
+  for (int h = 0; h < H; ++h) {
+    float s = 0.f;
+    for (int e = 0; e < dh; ++e) s = fmaf(sq[h * dh + e], ldv<T>(K.p, koff + h * dh + e), s);
+    acc += expf(s * scale - lse[((long long)b * H + h) * Sq + i]);
+  }
+  out[((long long)b * Sq + i) * Sk + j] = acc / (float)H;
+}
+
 #define DX_ATTN_DISPATCH(T, CALL)                                                     \
   switch (dh) {                                                                       \
     case 4: return CALL(T, 4, 1);                                                     \
@@ -412,6 +437,23 @@ int dx_attn_bwd(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_
 #define CALL_BWD(T, DH, TPQ) launch_bwd<T, DH, TPQ>(Q, K, V, O, GO, DQ, DK, DV, lse, D_ws, B, H, Sq, Sk, scale, drop, seed_dev, st)
   if (dtype == DX_BF16) { DX_ATTN_DISPATCH(bf16, CALL_BWD) } else { DX_ATTN_DISPATCH(float, CALL_BWD) }
 #undef CALL_BWD
+}
+
+int dx_attn_probs_mean(const void* q, int64_t q_bs, int64_t q_rs, const void* k, int64_t k_bs, int64_t k_rs, const float* lse,
+                       float* out, int B, int H, int Sq, int Sk, int dh, int dtype, void* stream) {
+  DX_CHECK_ARG(q && k && lse && out, "dx_attn_probs_mean: null tensor");
+  DX_CHECK_ARG(B > 0 && H > 0 && Sq > 0 && Sk > 0 && dh > 0, "dx_attn_probs_mean: empty problem");
+  DX_CHECK_ARG(B <= 65535 && Sq <= 65535, "dx_attn_probs_mean: B and Sq must be <= 65535");
+  DX_CHECK_ARG((size_t)H * dh * sizeof(float) <= 48 * 1024, "dx_attn_probs_mean: H*dh must be <= 12288");
+  cudaStream_t st = (cudaStream_t)stream;
+  AttnView Q{q, q_bs, q_rs}, K{k, k_bs, k_rs};
+  const float scale = 1.f / sqrtf((float)dh);
+  const dim3 grid(dx_ceil_div(Sk, NTH), Sq, B);
+  const size_t smem = (size_t)H * dh * sizeof(float);
+  if (dtype == DX_BF16) attn_probs_mean_kernel<bf16><<<grid, NTH, smem, st>>>(Q, K, lse, out, H, Sq, Sk, dh, scale);
+  else attn_probs_mean_kernel<float><<<grid, NTH, smem, st>>>(Q, K, lse, out, H, Sq, Sk, dh, scale);
+  DX_LAUNCH_CHECK();
+  return DX_OK;
 }
 
 int dx_rowdot_scale(const void* a, void* g, const float* row_scale, float* rowdot, int N, int C, int dtype, void* stream) {

@@ -268,6 +268,54 @@ __global__ void __launch_bounds__(NT) colsum_vec_kernel(const T* __restrict__ X,
   }
 }
 
+// strip variant (round 2): a warp owns a 32-vector (256-column) strip, the 8 warps of a CTA interleave over the rows of the
+// CTA's row chunk, 4 rows in flight per thread; the 8 partial strips are summed through shared memory and leave as one
+// atomicAdd per column.  Narrow matrices (N = 512: two strips) keep every thread busy and the grid is sized by rows, not by
+// columns — the single-row-per-iteration kernel above ran the path's bias / positional sums at 3.4 TB/s.
+constexpr int CS_WARPS = 8, CS_UNROLL = 4;
+template <typename T>
+__global__ void __launch_bounds__(32 * CS_WARPS) colsum_strip_kernel(const T* __restrict__ X, long long ld, int M, long long N,
+                                                                    float* __restrict__ out, int direct, int rows_per_block) {
+  __shared__ float part[CS_WARPS][32][9];   // +1: conflict-free column reads
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long n = ((long long)blockIdx.x * 32 + lane) * 8;
+  const int m0 = blockIdx.y * rows_per_block;
+  const int m1 = min(M, m0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (n < N) {
+    const T* p = X + n;
+    int m = m0 + w;
+    for (; m + (CS_UNROLL - 1) * CS_WARPS < m1; m += CS_UNROLL * CS_WARPS) {
+      float v[CS_UNROLL][8];
+#pragma unroll
+      for (int u = 0; u < CS_UNROLL; ++u) dx_ld8(p + (long long)(m + u * CS_WARPS) * ld, v[u]);
+#pragma unroll
+      for (int u = 0; u < CS_UNROLL; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
+    }
+    for (; m < m1; m += CS_WARPS) {
+      float v[8];
+      dx_ld8(p + (long long)m * ld, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[w][lane][j] = acc[j];
+  __syncthreads();
+  // thread t sums column t of the strip over the 8 warps
+  const int c = threadIdx.x;               // 0 .. 255
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < CS_WARPS; ++k) s += part[k][c >> 3][c & 7];
+  const long long col = (long long)blockIdx.x * 256 + c;
+  if (col < N) {
+    if (direct) out[col] = s;
+    else atomicAdd(out + col, s);
+  }
+}
+
 // y (+)= alpha * x  over n elements (n % 8 == 0)
 template <typename T>
 __global__ void __launch_bounds__(NT) axpy_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec, float alpha,
@@ -396,6 +444,23 @@ int dx_colsum(const void* X, int64_t ld, int M, int64_t N, float* out, int accum
   cudaStream_t st = (cudaStream_t)stream;
   const long long esz = dtype == DX_BF16 ? 2 : 4;
   const bool vec = (N % 8 == 0) && ((uintptr_t)X % 16 == 0) && ((ld * esz) % 16 == 0);
+  static const bool v1 = [] { const char* e = getenv("DX_COLSUM_V1"); return e && atoi(e) != 0; }();   // A/B: the round-1 kernel
+  if (vec && !v1) {
+    const int strips = dx_ceil_div(N / 8, 32);
+    // row chunks: ~8 CTAs per SM over the whole grid, at least CS_UNROLL * CS_WARPS rows each
+    int gy = dx_ceil_div(148 * 8, strips);
+    const int max_gy = dx_ceil_div(M, CS_UNROLL * CS_WARPS);
+    if (gy > max_gy) gy = max_gy;
+    const int rpb = dx_ceil_div(M, gy);
+    gy = dx_ceil_div(M, rpb);
+    const int direct = (gy == 1 && !accumulate) ? 1 : 0;
+    if (gy > 1 && !accumulate) DX_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
+    dim3 grid(strips, gy);
+    if (dtype == DX_BF16) colsum_strip_kernel<bf16><<<grid, 32 * CS_WARPS, 0, st>>>((const bf16*)X, ld, M, N, out, direct, rpb);
+    else colsum_strip_kernel<float><<<grid, 32 * CS_WARPS, 0, st>>>((const float*)X, ld, M, N, out, direct, rpb);
+    DX_LAUNCH_CHECK();
+    return DX_OK;
+  }
   const int gx = vec ? dx_ceil_div(N / 8, NT) : dx_ceil_div(N, NT);
   // enough row-splits to fill the machine when N is small
   int gy = 1;

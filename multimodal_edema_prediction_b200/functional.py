@@ -190,22 +190,25 @@ class AttentionFn(torch.autograd.Function):
     drop_p > 0: dropout on the attention probabilities (nn.MultiheadAttention(dropout=...) in training mode)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, heads, drop_p=0.0):
+    def forward(ctx, q, k, v, heads, drop_p=0.0, return_lse=False):
         drop = (drop_p, ops.drop_seed("attn", drop_p, (q.shape[0], heads, q.shape[1], k.shape[1]))) if drop_p > 0 else None
         o, lse = ops.attn_fwd(q, k, v, heads, drop)
         ctx.heads, ctx.drop = heads, drop
         ctx.save_for_backward(q, k, v, o, lse)
+        if return_lse:               # row log-sum-exp [B,h,Sq] for ops.attn_probs_mean (attention-map visualisation)
+            ctx.mark_non_differentiable(lse)
+            return o, lse
         return o
 
     @staticmethod
-    def backward(ctx, go):
+    def backward(ctx, go, *_):
         q, k, v, o, lse = ctx.saved_tensors
         go = go.contiguous()
         dq, dk, dv = torch.empty_like(q, memory_format=torch.contiguous_format), \
             torch.empty_like(k, memory_format=torch.contiguous_format), \
             torch.empty_like(v, memory_format=torch.contiguous_format)
         ops.attn_bwd(q, k, v, o, go, lse, ctx.heads, dq, dk, dv, ctx.drop)
-        return dq, dk, dv, None, None
+        return dq, dk, dv, None, None, None
 
 
 class DropoutFn(torch.autograd.Function):

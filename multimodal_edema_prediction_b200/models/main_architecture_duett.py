@@ -55,7 +55,9 @@ class _MHA(nn.Module):
         nn.init.xavier_uniform_(self.in_proj_weight)
         nn.init.zeros_(self.out_proj.bias)
 
-    def forward(self, q_in, kv_in, residual=None, same_kv=False):
+    def forward(self, q_in, kv_in, residual=None, same_kv=False, need_weights=False):
+        """need_weights=True also returns the head-averaged attention probabilities [B,Sq,Sk] f32
+        (nn.MultiheadAttention(need_weights=True, average_attn_weights=True))."""
         d = self.embed_dim
         W, b = self.in_proj_weight, self.in_proj_bias
         if same_kv and q_in is kv_in:
@@ -65,8 +67,18 @@ class _MHA(nn.Module):
             q = linear(q_in, W[:d], b[:d])
             kv = linear(kv_in, W[d:], b[d:])
             k, v = kv[..., :d], kv[..., d:]
-        o = AttentionFn.apply(q, k, v, self.num_heads, float(self.dropout) if self.training else 0.0)
-        return linear(o, self.out_proj.weight, self.out_proj.bias, res=residual)
+        drop_p = float(self.dropout) if self.training else 0.0
+        if not need_weights:
+            o = AttentionFn.apply(q, k, v, self.num_heads, drop_p)
+            return linear(o, self.out_proj.weight, self.out_proj.bias, res=residual)
+        if drop_p > 0:
+            # torch returns the *dropped* probabilities here; the reference asks for maps at inference only
+            raise NotImplementedError("attention maps with attention dropout active: call .eval() first "
+                                      "(return_attn=True is the reference's inference-time visualisation path)")
+        o, lse = AttentionFn.apply(q, k, v, self.num_heads, 0.0, True)
+        with torch.no_grad():
+            attn_w = ops.attn_probs_mean(q.detach(), k.detach(), lse, self.num_heads)
+        return linear(o, self.out_proj.weight, self.out_proj.bias, res=residual), attn_w
 
 
 class _PerceiverBlock(nn.Module):
@@ -84,17 +96,21 @@ class _PerceiverBlock(nn.Module):
         self.dropout = dropout
 
     def forward(self, latents, kv, return_attn: bool = False):
-        if return_attn:
-            raise NotImplementedError("return_attn=True (attention-map visualisation) is not on the B200 hot path")
         q = layer_norm(latents, self.norm_q.weight, self.norm_q.bias)
         k = layer_norm(kv, self.norm_kv.weight, self.norm_kv.bias)
-        latents = self.attn(q, k, residual=latents)
+        attn_w = None
+        if return_attn:
+            latents, attn_w = self.attn(q, k, residual=latents, need_weights=True)
+        else:
+            latents = self.attn(q, k, residual=latents)
         f = layer_norm(latents, self.norm_ff.weight, self.norm_ff.bias)
         h = linear(f, self.ff[0].weight, self.ff[0].bias, ops.ACT_GELU)
         h = dropout(h, self.ff[2].p, self.training, "perceiver.ff")
         if self.ff[4].p > 0 and self.training:      # Dropout after the second Linear sits before the residual add
-            return latents + dropout(linear(h, self.ff[3].weight, self.ff[3].bias), self.ff[4].p, True, "perceiver.ff_out")
-        return linear(h, self.ff[3].weight, self.ff[3].bias, res=latents)
+            latents = latents + dropout(linear(h, self.ff[3].weight, self.ff[3].bias), self.ff[4].p, True, "perceiver.ff_out")
+        else:
+            latents = linear(h, self.ff[3].weight, self.ff[3].bias, res=latents)
+        return (latents, attn_w) if return_attn else latents
 
 
 class PatchDualPathologyPerceiver(nn.Module):
@@ -131,8 +147,6 @@ class PatchDualPathologyPerceiver(nn.Module):
         if ts_ablation not in ("full", "hourly_only", "rep_only"):
             raise ValueError(f"unknown ts_ablation={ts_ablation!r}; expected one of "
                              "{'full', 'hourly_only', 'rep_only'}")
-        if return_attn:
-            raise NotImplementedError("return_attn=True (attention-map visualisation) is not on the B200 hot path")
         B = ts_tokens.size(0)
         at = ts_tokens.dtype
         with torch.autocast("cuda", enabled=False):
@@ -146,9 +160,16 @@ class PatchDualPathologyPerceiver(nn.Module):
                 ts_kv = ts_all[:, -1:]
             ts_kv = ts_kv.contiguous()
             img_kv = img_patches_proj if img_patches_proj.dtype == at else cast(img_patches_proj, at)
-            I = self.img_cross(q0, img_kv)
+            img_attn = ts_attn = None
+            if return_attn:        # [B,K,N_patches] / [B,K,T or T+1 or 1] f32, head-averaged
+                I, img_attn = self.img_cross(q0, img_kv, return_attn=True)
+            else:
+                I = self.img_cross(q0, img_kv)
             I = self.img_self(I, I)
-            T_tok = self.ts_cross(q0, ts_kv)
+            if return_attn:
+                T_tok, ts_attn = self.ts_cross(q0, ts_kv, return_attn=True)
+            else:
+                T_tok = self.ts_cross(q0, ts_kv)
             T_tok = self.ts_self(T_tok, T_tok)
             If, Tf = cast(I, torch.float32), cast(T_tok, torch.float32)
             hi = self.image_head(If).squeeze(-1)
@@ -160,9 +181,12 @@ class PatchDualPathologyPerceiver(nn.Module):
             ts_correction = linear(c, ch[4].weight, None).squeeze(-1)
             img_logits, ts_logits, scaled_correction, fusion_logits = FusionLogitsFn.apply(
                 hi, ht, ts_correction, self.image_label_bias, self.temporal_label_bias, self.beta)
-        return {"img_logits": img_logits, "ts_logits": ts_logits, "fusion_logits": fusion_logits, "img_tokens": I,
-                "ts_tokens": T_tok, "fusion_tokens": T_tok, "ts_correction": ts_correction,
-                "scaled_correction": scaled_correction}
+        out = {"img_logits": img_logits, "ts_logits": ts_logits, "fusion_logits": fusion_logits, "img_tokens": I,
+               "ts_tokens": T_tok, "fusion_tokens": T_tok, "ts_correction": ts_correction,
+               "scaled_correction": scaled_correction}
+        if return_attn:
+            out["img_attn"], out["ts_attn"] = img_attn, ts_attn
+        return out
 
 
 class TeacherModel(nn.Module):
@@ -203,6 +227,9 @@ class TeacherModel(nn.Module):
         result = {"main_logit": out["fusion_logits"][:, 0], "img_logits": out["img_logits"],
                   "ts_logits": out["ts_logits"], "fusion_logits": out["fusion_logits"],
                   "ts_correction": out["ts_correction"], "scaled_correction": out["scaled_correction"]}
+        if return_attn:                # models/main_architecture_duett.py:1123-1128
+            for k in ("img_tokens", "ts_tokens", "fusion_tokens", "img_attn", "ts_attn"):
+                result[k] = out[k]
         return result
 
 

@@ -288,6 +288,21 @@ def attn_fwd(q, k, v, heads, drop=None):
     return o, lse
 
 
+def attn_probs_mean(q, k, lse, heads):
+    """Head-averaged attention probabilities [B,Sq,Sk] f32 from q [B,Sq,h*dh], k [B,Sk,h*dh] and the lse [B,h,Sq] of a
+    dropout-free attn_fwd call: nn.MultiheadAttention(need_weights=True, average_attn_weights=True)'s second output."""
+    B, Sq, D = q.shape
+    Sk = k.shape[1]
+    for t in (q, k, lse):
+        require_device(t)
+    assert k.dtype == q.dtype and lse.dtype == torch.float32 and lse.is_contiguous() and lse.shape == (B, heads, Sq)
+    out = torch.empty((B, Sq, Sk), device=q.device, dtype=torch.float32)
+    q_, qbs, qrs = _view3(q)
+    k_, kbs, krs = _view3(k)
+    _call("dx_attn_probs_mean", _p(q_), qbs, qrs, _p(k_), kbs, krs, _p(lse), _p(out), B, heads, Sq, Sk, D // heads, _dt(q))
+    return out
+
+
 def attn_bwd(q, k, v, o, go, lse, heads, dq, dk, dv, drop=None):
     B, Sq, D = q.shape
     Sk = k.shape[1]

@@ -196,6 +196,16 @@ def attn_fwd(q, k, v, heads, drop=None):
     return o.to(q.dtype).contiguous(), lse.contiguous()
 
 
+def attn_probs_mean(q, k, lse, heads):
+    """Contract of dx_attn_probs_mean: mean over heads of exp(q k^T / sqrt(dh) - lse)."""
+    B, Sq, D = q.shape
+    dh = D // heads
+    qh = q.float().reshape(B, Sq, heads, dh).transpose(1, 2)
+    kh = k.float().reshape(B, -1, heads, dh).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(dh)
+    return torch.exp(s - lse[..., None]).mean(1)
+
+
 def attn_bwd(q, k, v, o, go, lse, heads, dq, dk, dv, drop=None):
     with torch.enable_grad():
         qq, kk, vv = (t.detach().float().clone().requires_grad_(True) for t in (q, k, v))
@@ -517,7 +527,7 @@ def binary_auc(logits, labels, apply_sigmoid=True):
 
 
 EMULATED = ["binary_auc", "sum_n", "dropout", "rowdot_bias", "gemm_", "relayout_fwd", "relayout_bwd", "colsum", "axpy", "axpy_f32", "cast", "scalenorm_scale", "rowdot_scale",
-            "attn_fwd", "attn_bwd", "embed_fwd", "embed_bwd", "bn2d_fwd", "bn2d_bwd", "layernorm_fwd", "layernorm_bwd",
+            "attn_fwd", "attn_bwd", "attn_probs_mean", "embed_fwd", "embed_bwd", "bn2d_fwd", "bn2d_bwd", "layernorm_fwd", "layernorm_bwd",
             "mean_rows", "mean_rows_bwd", "gather_vec", "scatter_vec", "kd_loss", "bce_logits", "masked_mse_bce",
             "masked_bce_cols", "aux_residual_kl", "require_device", "act_bwd", "act_fwd", "scale_dev", "sum_div_acc", "fusion_logits",
             "fusion_logits_bwd", "adamw", "sumsq", "clip_factor", "cast_into", "ssl_mask"]

@@ -151,6 +151,47 @@ def test_teacher_step_matches_reference(emu):
     _grad_check(_ref_keyed_grads(teacher), G["grad"])
 
 
+def test_teacher_return_attn_matches_reference(emu):
+    """TeacherModel.forward(return_attn=True) in eval mode against the reference's own call (fixture g6,
+    oracle/make_golden_attn.py): attention maps, latent tokens, logits; the extra keys appear only when asked for."""
+    from multimodal_edema_prediction_b200.models.main_architecture_duett import (DuettFeatureExtractor,
+                                                                                 PatchDualPathologyPerceiver, TeacherModel)
+    G4, G = load("g4_teacher"), load("g6_teacher_attn")
+
+    class StubCXR(torch.nn.Module):
+        d_out = 16
+        def forward(self, pv):
+            return pv[:, 0], pv[:, 1:]
+
+    duett = DuettFeatureExtractor(pretrain=False, **KW)
+    perceiver = PatchDualPathologyPerceiver(7, duett.d_representation, d_latent=32, n_heads=4, dropout=0.1, head_hidden=16,
+                                            head_dropout=0.0)
+    teacher = TeacherModel(duett, StubCXR(), perceiver, patch_dual_pathology_mode=True, d_img=16)
+    teacher.load_state_dict(G4["param"], strict=True)
+    I = G4["in"]
+    args = (tuple(I["x_ts"]), tuple(I["x_static"]), tuple(I["bin_ends"]), I["pixel_values"])
+    teacher.eval()
+    with torch.no_grad():
+        out = teacher(*args, return_attn=True)
+        plain = teacher(*args)
+    assert set(out) - set(plain) == {"img_tokens", "ts_tokens", "fusion_tokens", "img_attn", "ts_attn"}
+    for k, v in G["out"].items():
+        assert out[k].shape == v.shape and rel(out[k], v) < TOL, k
+    assert out["img_attn"].dtype == torch.float32
+    for k in plain:
+        assert torch.equal(plain[k], out[k]), k
+    # ts_ablation variants change the key axis of ts_attn (T hourly tokens / T+1 with [REP] / the [REP] token alone)
+    tok = torch.randn(6, 5, duett.d_representation)
+    proj = torch.randn(6, 10, 32)
+    for abl, n in (("hourly_only", 4), ("full", 5), ("rep_only", 1)):
+        o = perceiver(tok, proj, return_attn=True, ts_ablation=abl)
+        assert o["ts_attn"].shape == (6, 7, n) and o["img_attn"].shape == (6, 7, 10)
+        assert torch.allclose(o["ts_attn"].sum(-1), torch.ones(6, 7), atol=1e-5)
+    teacher.train()
+    with pytest.raises(NotImplementedError):      # attention dropout active: torch would return the dropped maps
+        teacher(*args, return_attn=True)
+
+
 def test_state_dict_round_trip_and_tolerant_checkpoint_loading(emu, tmp_path):
     from multimodal_edema_prediction_b200.models.main_architecture_duett import DuettFeatureExtractor, load_duett_backbone
     G = load("g3_ssl")        # an SSL "checkpoint" in the reference's key layout

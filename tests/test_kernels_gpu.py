@@ -219,6 +219,23 @@ def test_cross_attention_few_queries(ops):
     assert rel(dq, rq) < 1e-4 and rel(dk, rk) < 1e-4 and rel(dv, rv) < 1e-4
 
 
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("B,Sq,Sk,D,H", [(2, 7, 1369, 256, 4), (3, 7, 24, 32, 4), (1, 129, 129, 128, 2), (2, 4, 130, 48, 4)])
+def test_attention_probs_mean(ops, dt, B, Sq, Sk, D, H):
+    """dx_attn_probs_mean (head-averaged attention maps of nn.MultiheadAttention(need_weights=True)) from the lse of
+    dx_attn_fwd: the perceiver's shapes (7 queries over 1369 patches / 24 hours), strided k views, a key count that is not a
+    multiple of the 128-thread block; rows sum to one."""
+    q = rnd(B, Sq, D, dtype=dt, seed=37, scale=0.7)
+    kv = rnd(B, Sk, 2 * D, dtype=dt, seed=38, scale=0.7)
+    k, v = kv[:, :, :D], kv[:, :, D:]
+    o, lse = ops.attn_fwd(q, k, v, H)
+    w = ops.attn_probs_mean(q, k, lse, H)
+    assert w.shape == (B, Sq, Sk) and w.dtype == torch.float32
+    rw = E.attn_probs_mean(*cpu(q, k), E.attn_fwd(*cpu(q, k, v), H)[1], H)
+    assert rel(w, rw) < (1e-4 if dt == torch.float32 else 5e-3)
+    assert float((w.sum(-1) - 1).abs().max()) < (1e-4 if dt == torch.float32 else 5e-3)
+
+
 def _embed_inputs(B, T, V, d, seed=40, ssl=True):
     g = torch.Generator().manual_seed(seed)
     obs = (torch.rand(B, T, V, generator=g) < 0.3).float()

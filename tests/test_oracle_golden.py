@@ -127,6 +127,21 @@ def test_teacher_patch_dual_step_matches_reference():
     _check_grads(Pt, G["grad"], "")
 
 
+def test_teacher_return_attn_matches_reference():
+    """Eval-mode TeacherModel.forward(return_attn=True) of the reference (oracle/make_golden_attn.py): head-averaged
+    attention maps of the two cross-attention blocks, latent tokens and logits."""
+    G4, G, cfg = load("g4_teacher"), load("g6_teacher_attn"), golden_cfg()
+    P = {k[len("duett."):]: v for k, v in G4["param"].items() if k.startswith("duett.")}
+    Pt = {k: v for k, v in G4["param"].items() if not k.startswith("duett.")}
+    I = G4["in"]
+    x_static, xs_ts, xs_times, _ = O.feats_to_input(I["x_ts"], I["x_static"], I["bin_ends"], cfg.T)
+    with torch.no_grad():
+        out = O.teacher_forward(P, Pt, cfg, x_static, xs_ts, xs_times, I["pixel_values"][:, 1:], training=False)
+    for k in ("main_logit", "img_logits", "ts_logits", "fusion_logits", "ts_correction", "scaled_correction", "img_tokens",
+              "ts_tokens", "img_attn", "ts_attn"):
+        assert out[k].shape == G["out"][k].shape and rel(out[k], G["out"][k]) < TOL, k
+
+
 def test_ff_inner_expression():
     # x_transformers: inner = int(dim * (d_ff / dim)) — float rounding can give d_ff - 1 (SURVEY §8 note)
     c = O.DuettConfig(3, 34, 24)

@@ -163,6 +163,36 @@ def test_golden_teacher_patch_dual(mode, tol):
     _grad_check(_ref_keyed_grads(teacher), G["grad"], tol, selfdev=None if mode == "fp32" else G["selfdev"]["global_grad"])
 
 
+@pytest.mark.parametrize("mode,tol", MODES)
+def test_golden_teacher_return_attn(mode, tol):
+    """Eval-mode TeacherModel.forward(return_attn=True) against the reference's own call (fixture g6,
+    oracle/make_golden_attn.py): head-averaged attention maps of the two cross-attention blocks, latent tokens, logits."""
+    from multimodal_edema_prediction_b200.models.main_architecture_duett import (DuettFeatureExtractor,
+                                                                                 PatchDualPathologyPerceiver, TeacherModel)
+    G4, G = load("g4_teacher"), load("g6_teacher_attn")
+
+    class StubCXR(torch.nn.Module):
+        d_out = 16
+        def forward(self, pv):
+            return pv[:, 0], pv[:, 1:]
+
+    duett = DuettFeatureExtractor(pretrain=False, precision=mode, **KW)
+    perceiver = PatchDualPathologyPerceiver(7, duett.d_representation, d_latent=32, n_heads=4, dropout=0.1, head_hidden=16,
+                                            head_dropout=0.0)
+    teacher = TeacherModel(duett, StubCXR(), perceiver, patch_dual_pathology_mode=True, d_img=16)
+    teacher.load_state_dict(G4["param"], strict=True)
+    teacher.cuda().eval()
+    I = G4["in"]
+    with torch.no_grad():
+        out = teacher(tuple(I["x_ts"]), tuple(I["x_static"]), tuple(I["bin_ends"]), I["pixel_values"].cuda(), return_attn=True)
+    assert out["img_attn"].shape == (6, 7, 10) and out["ts_attn"].shape == (6, 7, 4)
+    for k in ("img_attn", "ts_attn", "img_tokens", "ts_tokens"):
+        assert rel(out[k].float().cpu(), G["out"][k]) < tol, k
+    for k in ("main_logit", "img_logits", "ts_logits", "fusion_logits"):
+        assert rel(out[k].float().cpu(), G["out"][k]) < tol * 2, k
+    assert float((out["img_attn"].sum(-1) - 1).abs().max()) < 1e-2 and float((out["ts_attn"].sum(-1) - 1).abs().max()) < 1e-2
+
+
 def _oracle_vs_cuda_student(cfg, B, mode, tol, seed=0, pool="mean"):
     from multimodal_edema_prediction_b200.models.main_architecture_duett import DuettFeatureExtractor, StudentModel
     P = O.init_params(cfg, seed=seed)
