@@ -196,7 +196,9 @@ int dx_act_fwd(const void* x, void* out, int64_t n, int act, int dtype, void* st
 int dx_act_bwd(const void* g, const void* aux, void* out, int64_t n, int act, int dtype, void* stream);
 
 /* Pooling / gathers around the heads: mean over the T hourly tokens (models/main_architecture_duett.py:1228-1231,
- * duett/duett.py:297-298); row / column gathers of the SSL heads (duett/duett.py:291-296,310-313) and their scatter. */
+ * duett/duett.py:297-298); row / column gathers of the SSL heads (duett/duett.py:287-296,310-313) and their scatter.
+ * A negative offset selects nothing: its gathered row is zero and nothing is scattered for it (the zero-padded rows of
+ * pretrain_masked_steps > 1, duett/duett.py:291). */
 int dx_mean_rows(const void* x, float* y, int B, int T1, int T, int64_t E, int dtype, void* stream);
 int dx_mean_rows_bwd(const float* dy, void* dx, int B, int T1, int T, int64_t E, int dtype, void* stream);
 int dx_gather_vec(const void* src, const int64_t* offsets, float* out, int n, int L, int dtype, void* stream);
@@ -266,13 +268,14 @@ int dx_bin_events(const int* slot, const double* vals, const double* cnts, const
                   const double* stds, int B, int T, int V, float* x, void* stream);
 
 /* ---- SSL masking ------------------------------------------------------------------------------------------
- * Model.pretrain_prep_batch (duett/duett.py:189-237, pretrain_masked_steps == 1) as one launch.  The random draws stay on
- * the host (numpy Generator, same order as the reference: per sample one timestep then one variable, then the [B,V]
- * variable-dropout matrix) and arrive as index arrays: step [B] int32, ev [B] int32 (NULL = predict_events off),
- * keep [B,V] uint8 (NULL = pretrain_dropout 0).  xs [B,T,2V+1] f32 -> xc (masked copy), y_ts / y_mask [B,V] (values and
- * clipped counts of the masked timestep), y_ev / y_ev_mask [B,T] (the masked variable's column).  Bit-exact selection. */
-int dx_ssl_mask(const float* xs, const int* step, const int* ev, const unsigned char* keep, int B, int T, int V, float* xc,
-                float* y_ts, float* y_mask, float* y_ev, float* y_ev_mask, void* stream);
+ * Model.pretrain_prep_batch (duett/duett.py:189-237) as one launch.  The random draws stay on the host (numpy Generator,
+ * same order as the reference: per sample K = pretrain_masked_steps timesteps — one rng.choice call, with replacement when
+ * K > 1 — then one variable, then the [B,V] variable-dropout matrix) and arrive as index arrays: step [B,K] int32, ev [B]
+ * int32 (NULL = predict_events off), keep [B,V] uint8 (NULL = pretrain_dropout 0).  xs [B,T,2V+1] f32 -> xc (masked copy),
+ * y_ts / y_mask [B,K,V] (values and clipped counts of the masked timesteps, draw order, repeats included), y_ev / y_ev_mask
+ * [B,T] (the masked variable's column).  Bit-exact selection. */
+int dx_ssl_mask(const float* xs, const int* step, const int* ev, const unsigned char* keep, int B, int T, int V, int K,
+                float* xc, float* y_ts, float* y_mask, float* y_ev, float* y_ev_mask, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,7 @@ SIGNATURES = {
     "dx_clip_factor": [P, F, P, P],
     "dx_sum_n": [P, I, P, L, I, P],
     "dx_bin_events": [P, P, P, P, P, P, I, I, I, P, P],
-    "dx_ssl_mask": [P, P, P, P, I, I, I, P, P, P, P, P, P],
+    "dx_ssl_mask": [P, P, P, P, I, I, I, I, P, P, P, P, P, P],
     "dx_binary_auc": [P, P, L, P, P, L, I, P, P],
     "dx_act_bwd": [P, P, P, L, I, I, P],
     "dx_act_fwd": [P, P, L, I, I, P],

@@ -34,13 +34,14 @@ __global__ void __launch_bounds__(256) bin_events_kernel(const int* __restrict__
   }
 }
 
-// SSL masking of Model.pretrain_prep_batch (duett/duett.py:189-237, pretrain_masked_steps == 1) driven by the host numpy-RNG
-// draws: step[b] = the masked timestep, ev[b] = the masked variable (-1: predict_events off), keep[b,v] = variable-dropout
-// draw (null: pretrain_dropout == 0).  One thread per cell of xs [B,T,C] (C = 2V+1) writes x_c and, for the cells of the
-// masked row / column, the targets.  Pure selection: bit-exact against the reference's index chain.
+// SSL masking of Model.pretrain_prep_batch (duett/duett.py:189-237) driven by the host numpy-RNG draws: step[b, 0..K) = the
+// masked timesteps (K = pretrain_masked_steps; drawn with replacement, so they may repeat), ev[b] = the masked variable
+// (null: predict_events off), keep[b,v] = variable-dropout draw (null: pretrain_dropout == 0).  One thread per cell of xs
+// [B,T,C] (C = 2V+1) writes x_c and, for the cells of the masked rows / column, the targets (y_ts / y_mask [B,K,V] in draw
+// order, a repeated step fills each of its slots).  Pure selection: bit-exact against the reference's index chain.
 __global__ void __launch_bounds__(256) ssl_mask_kernel(const float* __restrict__ xs, const int* __restrict__ step,
                                                        const int* __restrict__ ev, const unsigned char* __restrict__ keep, int B,
-                                                       int T, int V, float* __restrict__ xc, float* __restrict__ y_ts,
+                                                       int T, int V, int K, float* __restrict__ xc, float* __restrict__ y_ts,
                                                        float* __restrict__ y_mask, float* __restrict__ y_ev,
                                                        float* __restrict__ y_ev_mask) {
   const int C = 2 * V + 1;
@@ -50,20 +51,25 @@ __global__ void __launch_bounds__(256) ssl_mask_kernel(const float* __restrict__
     const int t = (int)((i / C) % T);
     const int b = (int)(i / ((long long)C * T));
     const float x = xs[i];
-    const int st = step[b], e = ev ? ev[b] : -1;
+    const int* st = step + (long long)b * K;
+    const int e = ev ? ev[b] : -1;
     float o = x;
-    if (t == st) {                                   // x_c[b, st, :] = 0, flag column = 1; targets of the masked timestep
+    for (int j = 0; j < K; ++j) {
+      if (t != st[j]) continue;                      // x_c[b, st, :] = 0, flag column = 1; targets of the masked timestep
       o = c == C - 1 ? 1.f : 0.f;
-      if (c < V) y_ts[(long long)b * V + c] = x;
-      else if (c < 2 * V) y_mask[(long long)b * V + (c - V)] = fminf(fmaxf(x, 0.f), 1.f);
+      if (c < V) y_ts[((long long)b * K + j) * V + c] = x;
+      else if (c < 2 * V) y_mask[((long long)b * K + j) * V + (c - V)] = fminf(fmaxf(x, 0.f), 1.f);
     }
     if (e >= 0) {                                    // x_c[b, :, e] = 0, x_c[b, :, e+V] = -1; targets of the masked variable
       if (c == e) { o = 0.f; y_ev[(long long)b * T + t] = x; }
       else if (c == e + V) { o = -1.f; y_ev_mask[(long long)b * T + t] = fminf(fmaxf(x, 0.f), 1.f); }
     }
-    if (keep && c < 2 * V && o != -1.f) {            // variable dropout: observed-at-the-masked-step variables may be dropped
+    if (keep && c < 2 * V && o != -1.f) {            // variable dropout: observed-at-a-masked-step variables may be dropped
       const int v = c < V ? c : c - V;
-      const float m = fminf(fmaxf(xs[((long long)b * T + st) * C + V + v], 0.f), 1.f);
+      // K == 1: 1 - y_ts_masks;  K > 1: 1 - y_ts_masks.sum(dim=1).clip(0, 1)   (duett/duett.py:229-232)
+      float m = 0.f;
+      for (int j = 0; j < K; ++j) m += fminf(fmaxf(xs[((long long)b * T + st[j]) * C + V + v], 0.f), 1.f);
+      if (K > 1) m = fminf(fmaxf(m, 0.f), 1.f);
       const bool kp = (1.f - m) != 0.f || keep[(long long)b * V + v] != 0;
       if (!kp) o = 0.f * o;                          // the reference multiplies by the boolean (keeps -0 / NaN semantics)
     }
@@ -75,14 +81,14 @@ __global__ void __launch_bounds__(256) ssl_mask_kernel(const float* __restrict__
 
 extern "C" {
 
-int dx_ssl_mask(const float* xs, const int* step, const int* ev, const unsigned char* keep, int B, int T, int V, float* xc,
-                float* y_ts, float* y_mask, float* y_ev, float* y_ev_mask, void* stream) {
-  DX_CHECK_ARG(xs && step && xc && y_ts && y_mask && B > 0 && T > 0 && V > 0, "dx_ssl_mask: bad arguments");
+int dx_ssl_mask(const float* xs, const int* step, const int* ev, const unsigned char* keep, int B, int T, int V, int K,
+                float* xc, float* y_ts, float* y_mask, float* y_ev, float* y_ev_mask, void* stream) {
+  DX_CHECK_ARG(xs && step && xc && y_ts && y_mask && B > 0 && T > 0 && V > 0 && K > 0, "dx_ssl_mask: bad arguments");
   DX_CHECK_ARG(!ev || (y_ev && y_ev_mask), "dx_ssl_mask: event targets missing");
   const long long n = (long long)B * T * (2 * V + 1);
   long long gl = (n + 255) / 256;
   const int grid = (int)(gl < 148 * 16 ? gl : 148 * 16);
-  ssl_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xs, step, ev, keep, B, T, V, xc, y_ts, y_mask, y_ev, y_ev_mask);
+  ssl_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xs, step, ev, keep, B, T, V, K, xc, y_ts, y_mask, y_ev, y_ev_mask);
   DX_LAUNCH_CHECK();
   return DX_OK;
 }

@@ -54,23 +54,25 @@ __global__ void __launch_bounds__(NT) mean_rows_bwd_kernel(const float* __restri
   }
 }
 
-// out[i, 0:L] = src[off[i] : off[i]+L]   (TI -> f32)
+// out[i, 0:L] = src[off[i] : off[i]+L]   (TI -> f32); off[i] < 0: a zero row
 template <typename TI>
 __global__ void __launch_bounds__(NT) gather_vec_kernel(const TI* __restrict__ src, const long long* __restrict__ off,
                                                        float* __restrict__ out, int n, int L) {
   const long long tot = (long long)n * L;
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < tot; i += (long long)gridDim.x * NT) {
     const int r = (int)(i / L), j = (int)(i % L);
-    out[i] = dx_ld(src + off[r] + j);
+    const long long o = off[r];
+    out[i] = o < 0 ? 0.f : dx_ld(src + o + j);
   }
 }
-// dst[off[i] : off[i]+L] (+)= src[i, 0:L]   (f32 -> TO); offsets must not overlap
+// dst[off[i] : off[i]+L] (+)= src[i, 0:L]   (f32 -> TO); offsets must not overlap; off[i] < 0: row skipped
 template <typename TO>
 __global__ void __launch_bounds__(NT) scatter_vec_kernel(const float* __restrict__ src, const long long* __restrict__ off,
                                                         TO* __restrict__ dst, int n, int L, int accumulate) {
   const long long tot = (long long)n * L;
   for (long long i = (long long)blockIdx.x * NT + threadIdx.x; i < tot; i += (long long)gridDim.x * NT) {
     const int r = (int)(i / L), j = (int)(i % L);
+    if (off[r] < 0) continue;
     TO* p = dst + off[r] + j;
     dx_st(p, accumulate ? dx_ld(p) + src[i] : src[i]);
   }

@@ -176,8 +176,8 @@ class Model(nn.Module):
                                       "1-hidden-layer embedding MLPs")
         if d_embedding % 8 or d_embedding % n_transformer_head:
             raise ValueError("d_embedding must be a multiple of 8 and of n_transformer_head")
-        if pretrain_masked_steps != 1:
-            raise NotImplementedError("pretrain_masked_steps > 1 is not implemented")
+        if int(pretrain_masked_steps) < 1:
+            raise ValueError("pretrain_masked_steps must be >= 1")
         self.lr, self.weight_decay = lr, weight_decay
         self.d_time_series_num, self.d_target, self.d_embedding = d_time_series_num, d_target, d_embedding
         self.max_len, self.pretrain = max_len, pretrain
@@ -402,32 +402,45 @@ class Model(nn.Module):
         return out
 
     def pretrain_prep_batch(self, x, batch_size):
-        """SSL masking with the host numpy RNG, byte-identical to duett/duett.py:189-237 (same draw order: per sample one
-        timestep then one variable, then the [B,V] variable-dropout matrix); index work vectorised on the host."""
+        """SSL masking with the host numpy RNG, byte-identical to duett/duett.py:189-237 (same draw order: per sample the
+        timestep(s) then one variable, then the [B,V] variable-dropout matrix); index work vectorised on the host.
+        pretrain_masked_steps = k > 1 (:199-203): k timesteps per sample in ONE rng.choice call, with replacement; targets
+        become [B,k,V] in draw order.  Every sample then needs >= max(2, k) timesteps — for shorter ones the reference's
+        targets are ragged and its torch.stack raises."""
         xs_static, xs_ts, xs_times, n_timesteps = self.feats_to_input(x, batch_size)
         V = (xs_ts.shape[2] - 1) // 2
         B = xs_ts.shape[0]
+        k = int(self.pretrain_masked_steps)
         steps, evs = [], []
         for n in n_timesteps:
-            steps.append(n if n < 2 else int(self.rng.choice(np.arange(0, n))))
+            if k > 1:
+                if n < max(2, k):
+                    raise ValueError(f"pretrain_masked_steps={k} needs at least {max(2, k)} timesteps in every sample "
+                                     f"(got {n}): the reference's ragged targets cannot be stacked")
+                steps.append([int(i) for i in self.rng.choice(np.arange(n), size=k)])
+            else:
+                steps.append(n if n < 2 else int(self.rng.choice(np.arange(0, n))))
             if self.predict_events:
                 evs.append(int(self.rng.choice(np.arange(0, self.d_time_series_num))))
         dev = xs_ts.device
-        if any(st >= xs_ts.shape[1] for st in steps):
+        if k == 1 and any(st >= xs_ts.shape[1] for st in steps):
             raise IndexError("pretrain_prep_batch: a sample has fewer than 2 timesteps")      # the reference's xs_ts[i][step] raises
         # the draws go up as ONE small pinned index block ([2,B] int32 + [B,V] uint8) and one kernel does the selection
         # (duett/duett.py:198-233: targets, masked copy, event column, variable dropout) — SURVEY §8f-2
         keep = None
         if self.pretrain_dropout > 0:
             keep = np.ascontiguousarray(self.rng.random((batch_size, V)) > self.pretrain_dropout).view(np.uint8)
-        idx = torch.tensor([steps, evs if self.predict_events else [0] * B], dtype=torch.int32)
+        # one index block: row 0 = the masked variable, rows 1..k = the masked timestep(s)
+        steps_kb = [steps] if k == 1 else [list(col) for col in zip(*steps)]
+        idx = torch.tensor([evs if self.predict_events else [0] * B] + steps_kb, dtype=torch.int32)
         if dev.type == "cuda":
             idx = idx.pin_memory().to(dev, non_blocking=True)
             keep_d = None if keep is None else torch.from_numpy(keep).pin_memory().to(dev, non_blocking=True)
         else:
             keep_d = None if keep is None else torch.from_numpy(keep)
+        step_d = idx[1] if k == 1 else idx[1:].t().contiguous()                  # [B] or [B,k]
         x_c, y_ts, y_ts_masks, y_events, y_events_mask = ops.ssl_mask(
-            xs_ts.float().contiguous(), idx[0], idx[1] if self.predict_events else None, keep_d)
+            xs_ts.float().contiguous(), step_d, idx[0] if self.predict_events else None, keep_d)
         if not self.predict_events:
             y_events, y_events_mask = [], []
         return (xs_static, x_c, xs_times, n_timesteps), y_ts, y_ts_masks, y_events, y_events_mask
@@ -494,6 +507,19 @@ class Model(nn.Module):
         off = (torch.arange(B, device=transformed.device, dtype=torch.int64) * T1 + idx) * Ep
         return GatherVecFn.apply(transformed, off, Ep)
 
+    def _masked_rows(self, transformed, xs_feats):
+        """pretrain_masked_steps = k > 1 (duett/duett.py:287-293): per sample the rows of the DISTINCT masked timesteps in time
+        order, zero-padded to k rows -> [B*k, E'] f32.  Index glue on the [B,T] flag matrix; the gather kernel writes a zero
+        row for a negative offset (and its backward scatters nothing there)."""
+        B, T1, Ep = transformed.shape
+        k = int(self.pretrain_masked_steps)
+        flag = xs_feats[:, :, -1] > 0                                             # [B,T]
+        order = torch.argsort(flag.to(torch.int8), dim=1, descending=True, stable=True)[:, :k]   # masked steps first, in time order
+        valid = torch.arange(k, device=flag.device)[None, :] < flag.sum(1, keepdim=True)
+        ar = torch.arange(B, device=flag.device, dtype=torch.int64)[:, None]
+        off = torch.where(valid, (ar * T1 + order) * Ep, torch.full_like(order, -1))
+        return GatherVecFn.apply(transformed, off.reshape(-1).contiguous(), Ep)
+
     def forward(self, x, pretrain=False, representation=False):
         from ..functional import MeanRowsFn
         xs_static, xs_feats, xs_times, n_timesteps = x
@@ -503,6 +529,8 @@ class Model(nn.Module):
         with torch.autocast("cuda", enabled=False):
             if self.fusion_method == 'rep_token':
                 z = self._row(transformed, T)
+            elif self.fusion_method == 'masked_embed' and self.pretrain_masked_steps > 1:
+                z = self._masked_rows(transformed, xs_feats)            # [B*k,E'], zero rows where a draw repeated
             elif self.fusion_method == 'masked_embed':
                 step = (xs_feats[:, :, -1] == 1).float().argmax(1)      # index glue on a [B,T] flag matrix
                 z = self._row(transformed, step)
@@ -510,11 +538,15 @@ class Model(nn.Module):
                 z = MeanRowsFn.apply(transformed, T)
             else:
                 raise ValueError(self.fusion_method)
+            ks = self.pretrain_masked_steps if self.fusion_method == 'masked_embed' else 1
             if representation:
-                return z
+                return z.view(B, ks, -1) if ks > 1 else z
             if pretrain:
                 y_hat_presence = self.pretrain_presence_proj(z).squeeze() if self.pretrain_presence else None
                 y_hat_value = self.pretrain_value_proj(z).squeeze(1) if self.pretrain_value else None
+                if ks > 1:       # the heads ran on all B*k rows (their BatchNorm sees the zero-padded rows, like the reference's)
+                    y_hat_presence = None if y_hat_presence is None else y_hat_presence.reshape(B, ks, -1)
+                    y_hat_value = None if y_hat_value is None else y_hat_value.reshape(B, ks, -1)
                 y_hat_events, y_hat_events_presence = None, None
                 if self.predict_events:
                     var = (xs_feats[:, 0, V:2 * V] == -1).float().argmax(1)             # masked variable per sample
@@ -525,6 +557,9 @@ class Model(nn.Module):
                     y_hat_events_presence = self.predict_events_presence_proj(z_events).squeeze() \
                         if self.pretrain_presence else None
                 return y_hat_value, y_hat_presence, y_hat_events, y_hat_events_presence
+            if ks > 1:
+                raise NotImplementedError("the supervised head on pretrain_masked_steps > 1 'masked_embed' features: the "
+                                          "reference's [B,k,E'] head input has no defined meaning (fine-tuning uses rep_token)")
             out = self.head(z).squeeze(1)
         if self.save_representation:
             return out, z
@@ -534,6 +569,15 @@ class Model(nn.Module):
     def _ssl_loss(self, outs, y, mask, y_events, y_events_mask):
         y_hat_value, y_hat_presence, y_hat_events, y_hat_events_presence = outs
         w = self.pretrain_presence_weight
+        if y.dim() == 3:
+            # pretrain_masked_steps = k > 1: the reference averages the k per-step losses (duett/duett.py:338-349); every step
+            # has B*V terms, so that is the mean over all [B,k,V] terms = the same kernel on B*k rows
+            if y_hat_value is None or y_hat_value.shape != y.shape:
+                raise ValueError("pretrain_masked_steps > 1 needs fusion_method='masked_embed' (the reference's per-step "
+                                 "y_hat[:, i] indexing has no meaning for a [B,V] prediction)")
+            V = y.shape[-1]
+            y_hat_value, y, mask = y_hat_value.reshape(-1, V), y.reshape(-1, V), mask.reshape(-1, V)
+            y_hat_presence = None if y_hat_presence is None else y_hat_presence.reshape(-1, V)
         loss = MaskedMseBceFn.apply(y_hat_value, y_hat_presence, y, mask, w)
         if self.predict_events:
             loss = loss + MaskedMseBceFn.apply(y_hat_events, y_hat_events_presence, y_events, y_events_mask, w)

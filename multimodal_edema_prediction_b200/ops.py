@@ -581,14 +581,19 @@ def bin_events(slot, vals, cnts, row_start, means, stds, T):
 
 
 def ssl_mask(xs, step, ev, keep):
-    """Model.pretrain_prep_batch's masking in one launch (duett/duett.py:189-237).  xs [B,T,2V+1] f32, step / ev [B] int32
-    (ev None: no event prediction), keep [B,V] uint8 or None -> (x_c, y_ts, y_ts_masks, y_events, y_events_mask)."""
+    """Model.pretrain_prep_batch's masking in one launch (duett/duett.py:189-237).  xs [B,T,2V+1] f32, step [B] or [B,K]
+    int32 (K = pretrain_masked_steps draws per sample, repeats allowed), ev [B] int32 (None: no event prediction), keep
+    [B,V] uint8 or None -> (x_c, y_ts, y_ts_masks, y_events, y_events_mask); y_ts / y_ts_masks are [B,V] for a 1-D step and
+    [B,K,V] for a 2-D one."""
     _chk(xs, torch.float32); _chk(step, torch.int32)
     B, T, C = xs.shape
     V = (C - 1) // 2
+    K = 1 if step.dim() == 1 else step.shape[1]
+    assert step.shape[0] == B and step.dim() in (1, 2)
     xc = torch.empty_like(xs)
-    y_ts = torch.empty((B, V), device=xs.device, dtype=torch.float32)
-    y_mask = torch.empty((B, V), device=xs.device, dtype=torch.float32)
+    tshape = (B, V) if step.dim() == 1 else (B, K, V)
+    y_ts = torch.empty(tshape, device=xs.device, dtype=torch.float32)
+    y_mask = torch.empty(tshape, device=xs.device, dtype=torch.float32)
     y_ev = y_ev_mask = None
     if ev is not None:
         _chk(ev, torch.int32)
@@ -597,7 +602,7 @@ def ssl_mask(xs, step, ev, keep):
     if keep is not None:
         _chk(keep, torch.uint8)
         assert keep.shape == (B, V)
-    _call("dx_ssl_mask", _p(xs), _p(step), _p(ev), _p(keep), B, T, V, _p(xc), _p(y_ts), _p(y_mask), _p(y_ev), _p(y_ev_mask))
+    _call("dx_ssl_mask", _p(xs), _p(step), _p(ev), _p(keep), B, T, V, K, _p(xc), _p(y_ts), _p(y_mask), _p(y_ev), _p(y_ev_mask))
     return xc, y_ts, y_mask, y_ev, y_ev_mask
 
 

@@ -302,13 +302,18 @@ def model_forward_supervised(P, cfg, xs_static, xs_feats, xs_times, fusion_metho
     return simple_head(P, "head", z, training, stats_out).squeeze(1)
 
 
-def model_forward_pretrain(P, cfg, xs_static, xs_feats, xs_times, training=True, stats_out=None):
-    """Model.forward(pretrain=True) with pretrain_masked_steps == 1 (duett/duett.py:291-316)."""
+def model_forward_pretrain(P, cfg, xs_static, xs_feats, xs_times, training=True, stats_out=None, masked_steps=1):
+    """Model.forward(pretrain=True) (duett/duett.py:284-316).  masked_steps > 1 (:287-293): the rows of the DISTINCT masked
+    timesteps in time order, zero-padded to masked_steps rows -> every head output gains a [masked_steps] axis."""
     tr, psi, event_masked = encode(P, cfg, xs_static, xs_feats, xs_times, training, stats_out, return_psi=True)
     B = tr.shape[0]
     ar = torch.arange(B, device=tr.device)
-    step = (xs_feats[:, :, -1] == 1).float().argmax(1)                    # the single masked timestep per sample
-    z = tr[ar, step]                                                      # [B,E']
+    if masked_steps > 1:
+        flag = F.pad(xs_feats[:, :, -1] > 0, (0, 1), value=False)         # [B,T+1]
+        z = torch.stack([F.pad(tr[b, flag[b]], (0, 0, 0, masked_steps - int(flag[b].sum()))) for b in range(B)])   # [B,k,E']
+    else:
+        step = (xs_feats[:, :, -1] == 1).float().argmax(1)                # the single masked timestep per sample
+        z = tr[ar, step]                                                  # [B,E']
     y_val = F.linear(z, P["pretrain_value_proj.0.weight"], P["pretrain_value_proj.0.bias"])
     y_pres = F.linear(z, P["pretrain_presence_proj.0.weight"], P["pretrain_presence_proj.0.bias"])
     var = event_masked[:, 0].float().argmax(1)                            # the single masked variable per sample
@@ -335,18 +340,29 @@ def feats_to_input(x_ts, x_static, times, max_len):
     return torch.stack(list(x_static)), xs_ts, xs_times, n_timesteps
 
 
-def pretrain_prep_batch(rng: np.random.Generator, cfg: DuettConfig, xs_ts, n_timesteps, pretrain_dropout=0.5):
-    """Model.pretrain_prep_batch for pretrain_masked_steps == 1, predict_events=True (duett/duett.py:189-237)."""
+def pretrain_prep_batch(rng: np.random.Generator, cfg: DuettConfig, xs_ts, n_timesteps, pretrain_dropout=0.5, masked_steps=1):
+    """Model.pretrain_prep_batch, predict_events=True (duett/duett.py:189-237).  masked_steps > 1 (:199-203): that many
+    timesteps per sample drawn WITH replacement (targets keep the draw order and the duplicates); every sample needs at
+    least max(2, masked_steps) timesteps (shorter ones make the reference's torch.stack fail on ragged targets)."""
     B, T, _ = xs_ts.shape
     V = cfg.V
     steps, evs = [], []
-    for n in n_timesteps:                       # RNG call order: (timestep, variable) per sample
-        steps.append(n if n < 2 else int(rng.choice(np.arange(0, n))))
+    for n in n_timesteps:                       # RNG call order: (timestep(s), variable) per sample
+        if masked_steps > 1:
+            if n < max(2, masked_steps):
+                raise ValueError("pretrain_masked_steps > 1 needs at least that many timesteps in every sample")
+            steps.append([int(i) for i in rng.choice(np.arange(n), size=masked_steps)])
+        else:
+            steps.append(n if n < 2 else int(rng.choice(np.arange(0, n))))
         evs.append(int(rng.choice(np.arange(0, V))))
     steps_t, evs_t = torch.tensor(steps), torch.tensor(evs)
     ar = torch.arange(B)
-    y_ts = xs_ts[ar, steps_t, :V].clone()
-    y_mask = xs_ts[ar, steps_t, V:2 * V].clip(0, 1)
+    if masked_steps > 1:
+        y_ts = xs_ts[ar[:, None], steps_t, :V].clone()                    # [B,k,V]
+        y_mask = xs_ts[ar[:, None], steps_t, V:2 * V].clip(0, 1)
+    else:
+        y_ts = xs_ts[ar, steps_t, :V].clone()
+        y_mask = xs_ts[ar, steps_t, V:2 * V].clip(0, 1)
     y_events = xs_ts[ar, :, evs_t].clone()
     y_events_mask = xs_ts[ar, :, evs_t + V].clip(0, 1)
     x = xs_ts.clone()
@@ -357,7 +373,7 @@ def pretrain_prep_batch(rng: np.random.Generator, cfg: DuettConfig, xs_ts, n_tim
         x[b, :, evs[b] + V] = -1.0
     if pretrain_dropout > 0:
         keep = torch.tensor(rng.random((B, V)) > pretrain_dropout)
-        keep = torch.logical_or(1 - y_mask, keep)
+        keep = torch.logical_or(1 - (y_mask.sum(dim=1).clip(0, 1) if masked_steps > 1 else y_mask), keep)
         keep = torch.cat((keep.tile(1, 2), torch.ones(B, 1)), dim=1)
         x = x * torch.logical_or(keep.unsqueeze(1), x == -1)
     return x, y_ts, y_mask, y_events, y_events_mask
@@ -367,7 +383,8 @@ def pretrain_prep_batch(rng: np.random.Generator, cfg: DuettConfig, xs_ts, n_tim
 # losses
 # ------------------------------------------------------------------------------------------------------------------
 def ssl_loss(y_val, y_pres, y_ev, y_ev_pres, y, mask, y_events, y_events_mask, presence_weight=0.2):
-    """duett/duett.py:337-358 (pretrain_masked_steps == 1)."""
+    """duett/duett.py:337-358.  With pretrain_masked_steps > 1 the targets are [B,k,V] and the reference averages the k
+    per-step losses (:338-349) — every step has B*V terms, so that is the mean over all [B,k,V] terms."""
     loss = F.mse_loss(y_val * mask, y * mask)
     loss = loss + F.binary_cross_entropy_with_logits(y_pres, mask) * presence_weight
     loss = loss + F.mse_loss(y_ev * y_events_mask, y_events * y_events_mask)

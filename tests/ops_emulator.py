@@ -330,18 +330,22 @@ def mean_rows_bwd(dy, T1, T, dtype):
 
 
 def gather_vec(src, offsets, Lv):
+    """A negative offset selects nothing: zero row."""
     flat = src.reshape(-1)
-    idx = offsets[:, None] + torch.arange(Lv)[None, :]
-    return flat[idx].float()
+    idx = offsets.clamp_min(0)[:, None] + torch.arange(Lv)[None, :]
+    return flat[idx].float() * (offsets >= 0)[:, None]
 
 
 def scatter_vec(src, offsets, dst, accumulate=True):
+    """Rows with a negative offset are skipped."""
     flat = dst.view(-1)
-    idx = (offsets[:, None] + torch.arange(src.shape[1])[None, :]).reshape(-1)
+    ok = offsets >= 0
+    idx = (offsets[ok][:, None] + torch.arange(src.shape[1])[None, :]).reshape(-1)
+    vals = src[ok].reshape(-1)
     if accumulate:
-        flat[idx] = (flat[idx].float() + src.reshape(-1)).to(dst.dtype)
+        flat[idx] = (flat[idx].float() + vals).to(dst.dtype)
     else:
-        flat[idx] = src.reshape(-1).to(dst.dtype)
+        flat[idx] = vals.to(dst.dtype)
 
 
 def _with_grad(fn, z, *args):
@@ -470,15 +474,19 @@ def adamw(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale_dev=None, g
 
 
 def ssl_mask(xs, step, ev, keep):
-    """Contract of dx_ssl_mask = the reference's index chain (duett/duett.py:198-233), written with torch indexing."""
+    """Contract of dx_ssl_mask = the reference's index chain (duett/duett.py:198-233), written with torch indexing; a 2-D
+    step [B,K] is the pretrain_masked_steps > 1 branch."""
     B, T, C = xs.shape
     V = (C - 1) // 2
     ar, st = torch.arange(B), step.long()
+    if st.dim() == 2:
+        ar = ar[:, None]
     y_ts = xs[ar, st, :V].clone()
     y_mask = xs[ar, st, V:2 * V].clip(0, 1)
     xc = xs.clone()
     xc[ar, st, :] = 0.
     xc[ar, st, -1] = 1.
+    ar = torch.arange(B)
     y_ev = y_ev_mask = None
     if ev is not None:
         e = ev.long()
@@ -487,7 +495,7 @@ def ssl_mask(xs, step, ev, keep):
         xc[ar, :, e] = 0.
         xc[ar, :, e + V] = -1.
     if keep is not None:
-        k = torch.logical_or(1 - y_mask, keep.bool())
+        k = torch.logical_or(1 - (y_mask.sum(dim=1).clip(0, 1) if st.dim() == 2 else y_mask), keep.bool())
         k = torch.cat((k.tile(1, 2), torch.ones((B, 1))), dim=1)
         xc = xc * torch.logical_or(k.unsqueeze(1), xc == -1)
     return xc, y_ts, y_mask, y_ev, y_ev_mask

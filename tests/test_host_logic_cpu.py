@@ -116,6 +116,40 @@ def test_ssl_step_matches_reference(emu):
     _grad_check(_ref_keyed_grads(model), G["grad"])
 
 
+def test_ssl_step_with_two_masked_steps_matches_reference(emu):
+    """pretrain_masked_steps = 2 against the reference's own step (fixture g7, oracle/make_golden_masked_steps.py): draws with
+    replacement bit-exact, [B,2,V] targets, distinct masked rows zero-padded to two, loss and every gradient."""
+    from multimodal_edema_prediction_b200.duett.duett import Model
+    G = load("g7_ssl_masked_steps")
+    model = Model(pretrain=True, seed=42, pretrain_masked_steps=2, **KW)
+    model.load_state_dict(G["param"], strict=True)
+    model.train()
+    I = G["in"]
+    x = (tuple(I["x_ts"]), tuple(I["x_static"]), list(I["bin_ends"]))
+    x_pre, y, mask, y_ev, y_ev_mask = model.pretrain_prep_batch(x, 6)
+    assert y.shape == (6, 2, 5) and torch.equal(x_pre[1], G["out"]["xs_ts_clipped"])
+    assert torch.equal(y, G["out"]["y"]) and torch.equal(mask, G["out"]["mask"])
+    assert torch.equal(y_ev, G["out"]["y_events"]) and torch.equal(y_ev_mask, G["out"]["y_events_mask"])
+    outs = model.forward(x_pre, pretrain=True)
+    for got, key in zip(outs, ("y_hat_value", "y_hat_presence", "y_hat_events", "y_hat_events_presence")):
+        assert got.shape == G["out"][key].shape and rel(got, G["out"][key]) < TOL, key
+    z = model.forward(x_pre, representation=True)
+    assert z.shape == (6, 2, model.d_embedding * 6)
+    dup = G["out"]["n_masked"] == 1                        # a repeated draw: the second row is the zero padding
+    assert bool(dup.any()) and float(z[dup, 1].abs().max()) == 0.0 and float(z[~dup, 1].abs().min()) > 0.0
+    model.rng = np.random.default_rng(42)
+    model.load_state_dict(G["param"])
+    loss = model.training_step((x, tuple([0.0] * 6)), 0)
+    assert rel(loss, G["out"]["loss"]) < TOL
+    loss.backward()
+    _grad_check(_ref_keyed_grads(model), G["grad"])
+    short = (tuple(t[:n] for t, n in zip(I["x_ts"], (4, 4, 1, 4, 4, 4))), x[1], [t[:n] for t, n in zip(I["bin_ends"], (4, 4, 1, 4, 4, 4))])
+    with pytest.raises(ValueError):
+        model.pretrain_prep_batch(short, 6)
+    with pytest.raises(ValueError):
+        Model(pretrain=True, pretrain_masked_steps=0, **KW)
+
+
 def test_teacher_step_matches_reference(emu):
     from multimodal_edema_prediction_b200.loss.losses_duett import DualPathologyLoss
     from multimodal_edema_prediction_b200.models.main_architecture_duett import (DuettFeatureExtractor,

@@ -334,6 +334,50 @@ def test_small_kernels(ops):
     assert rel(rd, rrd) < 1e-5 and rel(gr2, cgr) < 1e-6
 
 
+def test_gather_scatter_negative_offsets(ops):
+    """A negative offset selects nothing (the zero-padded rows of pretrain_masked_steps > 1): zero row out of the gather,
+    nothing written by the scatter."""
+    for dt in DT:
+        x = rnd(5, 7, 64, dtype=dt, seed=67)
+        off = torch.tensor([64, -1, 0, 1984, -1, 640], device="cuda")
+        g = ops.gather_vec(x, off, 64)
+        assert torch.equal(g.cpu(), E.gather_vec(x.cpu(), off.cpu(), 64)) and float(g[1].abs().max()) == 0.0
+        src = rnd(6, 64, seed=68)
+        dst, rdst = torch.zeros_like(x), torch.zeros(5, 7, 64, dtype=dt)
+        ops.scatter_vec(src, off, dst, accumulate=False)
+        E.scatter_vec(src.cpu(), off.cpu(), rdst, accumulate=False)
+        assert torch.equal(dst.cpu(), rdst)
+        ops.scatter_vec(src, off, dst, accumulate=True)
+        E.scatter_vec(src.cpu(), off.cpu(), rdst, accumulate=True)
+        assert torch.equal(dst.cpu(), rdst)
+
+
+@pytest.mark.parametrize("K", [1, 2, 3])
+@pytest.mark.parametrize("with_ev,with_keep", [(True, True), (False, True), (True, False)])
+def test_ssl_mask_kernel(ops, K, with_ev, with_keep):
+    """dx_ssl_mask against the reference's index chain (emulator), bit-exact: one or several masked timesteps per sample
+    (repeats included), masked variable, variable dropout, NaN cells and zero / fractional / multiple counts."""
+    B, T, V = 9, 6, 7
+    g = torch.Generator().manual_seed(70 + K)
+    vals = torch.randn(B, T, V, generator=g)
+    cnts = torch.randint(0, 4, (B, T, V), generator=g).float()
+    cnts[0, 0, 0], vals[1, 2, 3] = 0.5, float("nan")
+    xs = torch.cat([vals * (cnts > 0), cnts, torch.zeros(B, T, 1)], 2)
+    step = torch.randint(0, T, (B, K), generator=g, dtype=torch.int32)
+    if K > 1:
+        step[0, 1] = step[0, 0]                                    # a repeated draw
+    ev = torch.randint(0, V, (B,), generator=g, dtype=torch.int32) if with_ev else None
+    keep = (torch.rand(B, V, generator=g) > 0.5).to(torch.uint8) if with_keep else None
+    st = step[:, 0].contiguous() if K == 1 else step
+    want = E.ssl_mask(xs, st, ev, keep)
+    got = ops.ssl_mask(xs.cuda(), st.cuda(), None if ev is None else ev.cuda(), None if keep is None else keep.cuda())
+    assert got[1].shape == ((B, V) if K == 1 else (B, K, V))
+    for a, b in zip(got, want):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert torch.equal(torch.nan_to_num(a.cpu(), nan=12345.0), torch.nan_to_num(b, nan=12345.0))
+
+
 def test_loss_kernels(ops):
     B, K = 37, 7
     g = torch.Generator().manual_seed(70)

@@ -105,6 +105,30 @@ def test_ssl_step_matches_reference_including_host_rng():
     _check_grads(P, G["grad"])
 
 
+def test_ssl_step_with_two_masked_steps_matches_reference():
+    """pretrain_masked_steps = 2 (oracle/make_golden_masked_steps.py): draws with replacement, distinct masked rows zero-padded
+    to two rows, loss averaged over the steps (duett/duett.py:199-203, 287-293, 337-349)."""
+    G, cfg = load("g7_ssl_masked_steps"), golden_cfg()
+    P = _leaf(G["param"])
+    I = G["in"]
+    x_static, xs_ts, xs_times, n_t = O.feats_to_input(I["x_ts"], I["x_static"], I["bin_ends"], cfg.T)
+    rng = np.random.default_rng(42)
+    x, y, mask, y_ev, y_ev_mask = O.pretrain_prep_batch(rng, cfg, xs_ts, n_t, 0.5, masked_steps=2)
+    assert y.shape == (6, 2, cfg.V) and torch.equal(x, G["out"]["xs_ts_clipped"])
+    assert torch.equal(y, G["out"]["y"]) and torch.equal(mask, G["out"]["mask"])
+    assert torch.equal(y_ev, G["out"]["y_events"]) and torch.equal(y_ev_mask, G["out"]["y_events_mask"])
+    assert torch.equal((x[:, :, -1] > 0).sum(1), G["out"]["n_masked"]) and int(G["out"]["n_masked"].min()) == 1
+    outs = O.model_forward_pretrain(P, cfg, x_static, x, xs_times, masked_steps=2)
+    for got, key in zip(outs, ("y_hat_value", "y_hat_presence", "y_hat_events", "y_hat_events_presence")):
+        assert got.shape == G["out"][key].shape and rel(got, G["out"][key]) < TOL, key
+    loss = O.ssl_loss(*outs, y, mask, y_ev, y_ev_mask, 0.2)
+    assert rel(loss, G["out"]["loss"]) < TOL
+    loss.backward()
+    _check_grads(P, G["grad"])
+    with pytest.raises(ValueError):
+        O.pretrain_prep_batch(np.random.default_rng(0), cfg, xs_ts, [4, 4, 1, 4, 4, 4], 0.5, masked_steps=2)
+
+
 def test_teacher_patch_dual_step_matches_reference():
     G, cfg = load("g4_teacher"), golden_cfg()
     P = _leaf({k[len("duett."):]: v for k, v in G["param"].items() if k.startswith("duett.")})

@@ -131,6 +131,34 @@ def test_golden_ssl(mode, tol):
 
 
 @pytest.mark.parametrize("mode,tol", MODES)
+def test_golden_ssl_two_masked_steps(mode, tol):
+    """pretrain_masked_steps = 2 against the reference's own step (fixture g7, oracle/make_golden_masked_steps.py): host-RNG
+    draws with replacement -> dx_ssl_mask with K = 2 (bit-exact), distinct masked rows gathered and zero-padded
+    (dx_gather_vec with negative offsets), heads on B*2 rows, loss = mean of the per-step losses, every gradient."""
+    from multimodal_edema_prediction_b200.duett.duett import Model
+    G = load("g7_ssl_masked_steps")
+    model = Model(pretrain=True, seed=42, pretrain_masked_steps=2, precision=mode, **KW)
+    model.load_state_dict(G["param"], strict=True)
+    model.cuda().train()
+    I = G["in"]
+    x = (tuple(I["x_ts"]), tuple(I["x_static"]), list(I["bin_ends"]))
+    x_pre, y, mask, y_ev, y_ev_mask = model.pretrain_prep_batch(x, 6)
+    assert y.shape == (6, 2, 5) and torch.equal(x_pre[1].cpu(), G["out"]["xs_ts_clipped"])       # index / mask work: bit-exact
+    assert torch.equal(y.cpu(), G["out"]["y"]) and torch.equal(mask.cpu(), G["out"]["mask"])
+    assert torch.equal(y_ev.cpu(), G["out"]["y_events"]) and torch.equal(y_ev_mask.cpu(), G["out"]["y_events_mask"])
+    outs = model.forward(x_pre, pretrain=True)
+    for got, key in zip(outs, ("y_hat_value", "y_hat_presence", "y_hat_events", "y_hat_events_presence")):
+        assert got.shape == G["out"][key].shape and rel(got.cpu(), G["out"][key]) < tol * 2, key
+    model.rng = np.random.default_rng(42)
+    model.load_state_dict(G["param"])
+    model.cuda()
+    loss = model.training_step((x, tuple([0.0] * 6)), 0)
+    assert rel(loss.cpu(), G["out"]["loss"]) < tol
+    loss.backward()
+    _grad_check(_ref_keyed_grads(model), G["grad"], tol, selfdev=None if mode == "fp32" else G["selfdev"]["global_grad"])
+
+
+@pytest.mark.parametrize("mode,tol", MODES)
 def test_golden_teacher_patch_dual(mode, tol):
     from multimodal_edema_prediction_b200.loss.losses_duett import DualPathologyLoss
     from multimodal_edema_prediction_b200.models.main_architecture_duett import (DuettFeatureExtractor,
