@@ -152,6 +152,38 @@ class _Metric:
         return torch.tensor(roc_auc_score(y, p) if self.kind == "auroc" else average_precision_score(y, p))
 
 
+class _Staging:
+    """Pinned, double-buffered host staging for Model._upload.  One pair of flat buffers per (slot, dtype), sized for the
+    largest batch seen so far and viewed at the requested shape — ragged batches (a different pad length or a short last
+    batch every step) therefore do not accumulate one pinned allocation per distinct shape.  acquire() hands out the buffer
+    whose previous copy has completed (waits on its event if necessary); the caller records an event after enqueueing the
+    H2D copy and passes it to release()."""
+
+    def __init__(self, pin=True):
+        self.pin, self.slots = pin, {}
+
+    def acquire(self, slot, shape, dtype):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        s = self.slots.setdefault((slot, dtype), {"bufs": [None, None], "evts": [None, None], "i": 0})
+        i = s["i"]
+        s["i"] = 1 - i
+        if s["evts"][i] is not None:
+            s["evts"][i].synchronize()          # the copy that last used this buffer has completed
+            s["evts"][i] = None
+        if s["bufs"][i] is None or s["bufs"][i].numel() < n:
+            s["bufs"][i] = torch.empty(max(n, 1), dtype=dtype, pin_memory=self.pin)
+
+        def release(event):
+            s["evts"][i] = event
+
+        return s["bufs"][i][:n].view(shape), release
+
+    def pinned_bytes(self):
+        return sum(b.numel() * b.element_size() for s in self.slots.values() for b in s["bufs"] if b is not None)
+
+
 def pretrain_model(d_static_num, d_time_series_num, d_target, **kwargs):
     return Model(d_static_num, d_time_series_num, d_target, **kwargs)
 
@@ -384,21 +416,13 @@ class Model(nn.Module):
                 tensors = [t.to(dev, non_blocking=True) for t in tensors]
             return torch.stack(tensors).to(dev, non_blocking=True)
         shape = (len(tensors),) + tuple(t0.shape)
-        st = self.__dict__.setdefault("_staging", {})
-        key = (slot, shape, t0.dtype)
-        if key not in st:
-            st[key] = {"bufs": [torch.empty(shape, dtype=t0.dtype, pin_memory=True) for _ in range(2)],
-                       "evts": [None, None], "i": 0}
-        s = st[key]
-        i = s["i"]
-        s["i"] = 1 - i
-        if s["evts"][i] is not None:
-            s["evts"][i].synchronize()          # the copy that last used this buffer has completed
-        torch.stack(tensors, out=s["bufs"][i])
-        out = s["bufs"][i].to(dev, non_blocking=True)
+        st = self.__dict__.setdefault("_staging", _Staging(pin=True))
+        buf, release = st.acquire(slot, shape, t0.dtype)
+        torch.stack(tensors, out=buf)
+        out = buf.to(dev, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        s["evts"][i] = ev
+        release(ev)
         return out
 
     def pretrain_prep_batch(self, x, batch_size):

@@ -379,3 +379,33 @@ def test_evaluate_dual_pathology_surface(emu):
         assert abs(r["gap_i2f"] - (r["fus_auroc"] - r["img_auroc"])) < 1e-12 and abs(r["beta"] - [0.5, 1.0, 1.5][k]) < 1e-7
         fa.append(r["fus_auroc"])
     assert abs(res["main_auroc"] - sum(fa) / K) < 1e-12
+
+
+def test_upload_staging_is_bounded_by_the_largest_batch():
+    """Model._upload's pinned staging (duett._Staging, exercised here unpinned): two flat buffers per (slot, dtype) sized
+    for the largest batch seen, viewed at the requested shape; alternating buffers wait for the event of their last copy."""
+    from multimodal_edema_prediction_b200.duett.duett import _Staging
+
+    class Ev:
+        waited = 0
+
+        def synchronize(self):
+            Ev.waited += 1
+
+    st = _Staging(pin=False)
+    ptrs = []
+    for k, shape in enumerate([(4, 3, 5), (4, 2, 5), (2, 3, 5), (4, 3, 5), (6, 3, 5), (1, 1, 5)]):
+        buf, release = st.acquire("ts", shape, torch.float32)
+        assert tuple(buf.shape) == shape and buf.is_contiguous()
+        src = [torch.full(shape[1:], float(k + j)) for j in range(shape[0])]
+        torch.stack(src, out=buf)
+        assert torch.equal(buf, torch.stack(src))
+        ptrs.append(buf.data_ptr())
+        release(Ev())
+    # double buffering; a smaller batch reuses the allocation (2, 5), a larger one replaces it (3: 40 -> 60 elements, 4: 60 -> 90)
+    assert ptrs[0] != ptrs[1] and ptrs[2] == ptrs[0] and ptrs[3] != ptrs[1] and ptrs[5] == ptrs[3]
+    assert Ev.waited == 4                                                        # every reuse waited for the previous copy
+    assert st.pinned_bytes() == (6 * 3 * 5 + 4 * 3 * 5) * 4                      # the largest batch each buffer has held
+    buf64, _ = st.acquire("ts", (2, 2), torch.float64)                           # another dtype: its own pair
+    assert buf64.dtype == torch.float64 and len(st.slots) == 2
+
