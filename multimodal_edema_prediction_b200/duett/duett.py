@@ -408,8 +408,9 @@ class Model(nn.Module):
 
     def _upload(self, tensors, slot, dev):
         """Stack per-sample tensors and move them to the model's device with ONE copy.  Host inputs are stacked into a
-        pinned, double-buffered staging area (so the H2D copy is asynchronous); inputs already on the device are stacked
-        there (engine._move_lists moves them sample by sample like the reference does)."""
+        pinned, double-buffered staging area (_Staging, so the H2D copy is asynchronous; engine._move_lists leaves the
+        per-sample tuples on the host for exactly this); inputs already on the device (device-binned StayRows, callers that
+        moved their samples themselves) are stacked there."""
         t0 = tensors[0]
         if t0.is_cuda or dev.type != "cuda":
             if any(t.is_cuda != t0.is_cuda for t in tensors):          # device-binned x_ts next to host static / times

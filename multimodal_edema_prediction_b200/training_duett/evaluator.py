@@ -36,6 +36,8 @@ def binary_metrics(logits: torch.Tensor, y: torch.Tensor) -> dict:
     """{"auroc","auprc","n","pos_frac"} of sigmoid(logits) against y, computed on the device (one D2H read of 4 doubles)."""
     logits = _gather_all(logits.detach().reshape(-1).float())
     y = _gather_all(y.detach().reshape(-1).float())
+    if logits.numel() == 0:
+        return {"auroc": float("nan"), "auprc": float("nan"), "n": 0, "pos_frac": float("nan")}
     auroc, auprc, n_pos, n = ops.binary_auc(logits, y, apply_sigmoid=True).tolist()
     return {"auroc": float(auroc), "auprc": float(auprc), "n": int(n), "pos_frac": float(n_pos / n)}
 
@@ -53,7 +55,9 @@ def evaluate_binary(model, loader, device, forward_fn):
         logits_all.append(out["logits"].detach().reshape(-1).float())
         y_all.append(out["y"].detach().reshape(-1).float().to(out["logits"].device))
     if not logits_all:
-        return {"auroc": float("nan"), "auprc": float("nan"), "n": 0, "pos_frac": float("nan")}
+        # an empty shard still takes part in the cross-rank gather (returning early here would leave the other ranks waiting)
+        empty = torch.empty(0, device=torch.device(device), dtype=torch.float32)
+        return binary_metrics(empty, empty.clone())
     return binary_metrics(torch.cat(logits_all), torch.cat(y_all))
 
 

@@ -133,7 +133,10 @@ def _eval_worker(rank, world, port, q):
         z_all, y_all = torch.randn(37, generator=g), (torch.rand(37, generator=g) < 0.4).float()
         lo, hi = (0, 23) if rank == 0 else (23, 37)                 # uneven shards
         res = evaluator.binary_metrics(z_all[lo:hi], y_all[lo:hi])
-        q.put((rank, res))
+        # a rank whose loader is empty still joins the gather and reports the metric of the other rank's shard
+        loader = [] if rank == 1 else [{"logits": z_all, "y": y_all}]
+        res2 = evaluator.evaluate_binary(torch.nn.Identity(), loader, torch.device("cpu"), lambda m, b, d: b)
+        q.put((rank, res, res2))
     except Exception as ex:
         import traceback
         q.put((rank, "error", traceback.format_exc(), repr(ex)))
@@ -161,5 +164,6 @@ def test_evaluator_scores_the_whole_loader_on_every_rank_world2():
     want_pr = average_precision_score(y_all.numpy(), torch.sigmoid(z_all).numpy())
     for r in res:
         assert r[1] != "error", r
-        rank, m = r
+        rank, m, m2 = r
         assert m["n"] == 37 and abs(m["auroc"] - want_roc) < 1e-12 and abs(m["auprc"] - want_pr) < 1e-12, (rank, m)
+        assert m2["n"] == 37 and abs(m2["auroc"] - want_roc) < 1e-12, (rank, m2)

@@ -264,6 +264,8 @@ def test_evaluate_binary_surface(emu):
     assert abs(res["auroc"] - roc_auc_score(y, torch.sigmoid(z).numpy())) < 1e-12
     assert abs(res["auprc"] - average_precision_score(y, torch.sigmoid(z).numpy())) < 1e-12
     assert set(res) == {"auroc", "auprc", "n", "pos_frac"}
+    empty = evaluator.evaluate_binary(Dummy(), [], torch.device("cpu"), lambda m, b, dev: b)       # empty loader: NaNs, no launch
+    assert empty["n"] == 0 and empty["auroc"] != empty["auroc"] and set(empty) == set(res)
     for name in ("make_teacher_forward", "make_teacher_aux_forward", "make_student_forward"):
         assert callable(getattr(evaluator, name)())
 
