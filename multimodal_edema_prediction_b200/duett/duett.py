@@ -183,6 +183,14 @@ class _Staging:
     def pinned_bytes(self):
         return sum(b.numel() * b.element_size() for s in self.slots.values() for b in s["bufs"] if b is not None)
 
+    # a copied / pickled Model (copy.deepcopy for an EMA replica, torch.save(model)) starts with empty staging: the buffers
+    # are scratch and CUDA events cannot be copied
+    def __deepcopy__(self, memo):
+        return _Staging(self.pin)
+
+    def __reduce__(self):
+        return (_Staging, (self.pin,))
+
 
 def pretrain_model(d_static_num, d_time_series_num, d_target, **kwargs):
     return Model(d_static_num, d_time_series_num, d_target, **kwargs)

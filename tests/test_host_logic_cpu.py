@@ -410,4 +410,6 @@ def test_upload_staging_is_bounded_by_the_largest_batch():
     assert st.pinned_bytes() == (6 * 3 * 5 + 4 * 3 * 5) * 4                      # the largest batch each buffer has held
     buf64, _ = st.acquire("ts", (2, 2), torch.float64)                           # another dtype: its own pair
     assert buf64.dtype == torch.float64 and len(st.slots) == 2
+    import copy, pickle                                                          # copies of a Model start with empty staging
+    assert copy.deepcopy(st).slots == {} and pickle.loads(pickle.dumps(st)).slots == {} and copy.deepcopy(st).pin is False
 
