@@ -218,7 +218,7 @@ def test_c2_shape_student_kd_vs_oracle(mode, tol):
 @pytest.mark.parametrize("mode,tol", MODES)
 def test_c5_shape_vs_oracle(mode, tol):
     """BASELINE configs[4] stress shape (T=128, V=512, d=256; E=33 024, E'=131 328, dh=128) at B=2 against the CPU oracle
-    (replaces the bf16-vs-fp32 self-comparison of tests/c5_smoke.py): backbone + KD student head + StudentKDLoss, every
+    (replaces round 1's bf16-vs-fp32 self-comparison script): backbone + KD student head + StudentKDLoss, every
     quantity at the plain bound.  (The supervised head's BatchNorm over a batch of TWO samples is degenerate — x_hat = +-1
     whatever the input — so that head is exercised at C2/B=32 above, not here.)"""
     cfg = O.DuettConfig(d_static_num=24, d_time_series_num=512, n_timesteps=128, d_embedding=256, n_layers=2)
