@@ -599,21 +599,38 @@ class Model(nn.Module):
         return out
 
     # ---- Lightning-style steps (duett/duett.py:329-457) ----------------------------------------------------------------
+    @staticmethod
+    def _value_presence_loss(y_hat, p_hat, y, mask, w):
+        """mse(y_hat*m, y*m) + w * bce_with_logits(p_hat, m) with either head absent (pretrain_value / pretrain_presence
+        off, duett/duett.py:336-357).  One kernel computes both terms; an absent head is fed zeros so that its term is
+        exactly zero (zero prediction against a zero target, or presence weight 0)."""
+        if y_hat is None and p_hat is None:
+            return torch.zeros((), device=mask.device)
+        if y_hat is None:
+            z = torch.zeros_like(mask, dtype=torch.float32)
+            return MaskedMseBceFn.apply(z, p_hat, z, mask, w)
+        if p_hat is None:
+            return MaskedMseBceFn.apply(y_hat, torch.zeros_like(mask, dtype=torch.float32), y, mask, 0.0)
+        return MaskedMseBceFn.apply(y_hat, p_hat, y, mask, w)
+
     def _ssl_loss(self, outs, y, mask, y_events, y_events_mask):
         y_hat_value, y_hat_presence, y_hat_events, y_hat_events_presence = outs
         w = self.pretrain_presence_weight
         if y.dim() == 3:
             # pretrain_masked_steps = k > 1: the reference averages the k per-step losses (duett/duett.py:338-349); every step
             # has B*V terms, so that is the mean over all [B,k,V] terms = the same kernel on B*k rows
-            if y_hat_value is None or y_hat_value.shape != y.shape:
+            if any(t is not None and t.shape != y.shape for t in (y_hat_value, y_hat_presence)):
                 raise ValueError("pretrain_masked_steps > 1 needs fusion_method='masked_embed' (the reference's per-step "
                                  "y_hat[:, i] indexing has no meaning for a [B,V] prediction)")
             V = y.shape[-1]
-            y_hat_value, y, mask = y_hat_value.reshape(-1, V), y.reshape(-1, V), mask.reshape(-1, V)
+            y, mask = y.reshape(-1, V), mask.reshape(-1, V)
+            y_hat_value = None if y_hat_value is None else y_hat_value.reshape(-1, V)
             y_hat_presence = None if y_hat_presence is None else y_hat_presence.reshape(-1, V)
-        loss = MaskedMseBceFn.apply(y_hat_value, y_hat_presence, y, mask, w)
+        loss = self._value_presence_loss(y_hat_value, y_hat_presence, y, mask, w)
         if self.predict_events:
-            loss = loss + MaskedMseBceFn.apply(y_hat_events, y_hat_events_presence, y_events, y_events_mask, w)
+            # the event-value prediction is always computed (duett/duett.py:314) but only scored with pretrain_value (:351)
+            loss = loss + self._value_presence_loss(y_hat_events if self.pretrain_value else None, y_hat_events_presence,
+                                                    y_events, y_events_mask, w)
         return loss
 
     def _supervised_loss(self, y_hat, y):
