@@ -684,6 +684,11 @@ class Model(nn.Module):
         self.log('test_loss', loss, on_epoch=True, sync_dist=True, rank_zero_only=True)
         return loss, self.test_auroc, self.test_auprc
 
+    def on_train_epoch_end(self):
+        if not self.pretrain:                  # duett/duett.py:420-423
+            self.log('train_auroc', self.train_auroc, sync_dist=True, rank_zero_only=True)
+            self.log('train_ap', self.train_ap, sync_dist=True, rank_zero_only=True)
+
     def on_validation_epoch_end(self):
         if not self.pretrain:
             print(f'[epoch {self.current_epoch:>3d}] val_auroc={self.val_auroc.compute():.4f}  '

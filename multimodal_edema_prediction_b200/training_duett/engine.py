@@ -53,6 +53,44 @@ def _aux_residual(out, b, device, aux_residual_alpha):
     return torch.zeros((), device=device)
 
 
+def train_teacher_batch(batch, teacher, loss_fn, optimizer, device, accelerator=None, aux_alpha: float = 0.0):
+    """Binary teacher step for a teacher that returns the main logit, or a (main, aux) tuple whose auxiliary CXR-only logit
+    is scored with the same loss at weight aux_alpha (training_duett/engine.py:41-74).  The legacy TeacherModel modes that
+    return these are not built here (models/main_architecture_duett.py), the step itself is model-agnostic."""
+    teacher.train()
+    b = _move_lists(batch, device)
+    out = teacher(b["x_ts"], b["x_static"], b["bin_ends"], b["pixel_values"])
+    main_logit, aux_logit = out if isinstance(out, tuple) else (out, None)
+    y = b["y"].float()
+    main_loss = loss_fn(main_logit, y)
+    loss, aux_value = main_loss, 0.0
+    if aux_logit is not None:
+        aux_loss = loss_fn(aux_logit, y)
+        loss = main_loss + aux_alpha * aux_loss
+        aux_value = aux_loss.detach().item()
+    _backward_step(loss, optimizer, accelerator)
+    return {"loss": loss.detach().item(), "main_loss": main_loss.detach().item(), "aux_loss": aux_value,
+            "logits": main_logit.detach(), "y": b["y"].detach()}
+
+
+def train_teacher_pathology_batch(batch, teacher, path_loss_fn, optimizer, device, accelerator=None):
+    """Step of a `pathology_mode` teacher returning dict(main_logit, stage2_logits, stage4_logits), scored with
+    PathologyMultiLabelLoss (training_duett/engine.py:93-130).  Model-agnostic like train_teacher_batch."""
+    teacher.train()
+    b = _move_lists(batch, device)
+    out = teacher(b["x_ts"], b["x_static"], b["bin_ends"], b["pixel_values"])
+    if not isinstance(out, dict):
+        raise RuntimeError("pathology mode but TeacherModel did not return a dict")
+    losses = path_loss_fn(out["stage2_logits"], out["stage4_logits"], b["y_multi"], b["y_multi_mask"])
+    _backward_step(losses["total"], optimizer, accelerator)
+    res = {"loss": losses["total"].detach().item(), "stage2_total": losses["stage2_total"].item(),
+           "stage4_total": losses["stage4_total"].item(), "stage2_per": losses["stage2_per"].cpu(),
+           "stage4_per": losses["stage4_per"].cpu()}
+    res.update({k: out[k].detach() for k in ("main_logit", "stage2_logits", "stage4_logits")})
+    res.update({k: b[k].detach() for k in ("y", "y_multi", "y_multi_mask")})
+    return res
+
+
 def train_teacher_dual_pathology_batch(batch, teacher, path_loss_fn, optimizer, device, accelerator=None,
                                        aux_residual_alpha: float = 0.0):
     """training_duett/engine.py:135-190."""

@@ -189,3 +189,71 @@ def evaluate_dual_pathology(model, loader, device, pathology_labels, *, query_re
 
     return {"labels": list(pathology_labels), "n": int(y.shape[0]), "main_auroc": macro("fus_auroc"),
             "main_auprc": macro("fus_auprc"), "per_label": per_label}
+
+
+# ---- console tables (training_duett/trainer.py:24-25 imports these next to the evaluators) ---------------------------------
+def _cell(v, spec):
+    """One table cell; NaN / non-numeric -> right-aligned '--' of the column's width."""
+    width = int(spec.lstrip("+").split(".")[0])
+    try:
+        if v != v:
+            return "--".rjust(width)
+        return format(v, spec)
+    except (TypeError, ValueError):
+        return "--".rjust(width)
+
+
+# (header, result key, format spec, separator AFTER the column) of format_dual_pathology_gap_table, left to right
+_DUAL_COLS = (("imgROC", "img_auroc", "7.3f", " "), ("tsROC", "ts_auroc", "7.3f", " "), ("fusROC", "fus_auroc", "7.3f", " "),
+              ("gain", "gap_i2f", "+7.3f", "  "), ("imgAP", "img_auprc", "6.3f", " "), ("tsAP", "ts_auprc", "6.3f", " "),
+              ("fusAP", "fus_auprc", "6.3f", "  "), ("dBCE", "delta_bce", "+7.4f", "  "), ("|corr|", "mean_abs_corr", "7.4f", " "),
+              ("corr_r", "corr_residual", "+7.3f", "  "), ("beta", "beta", "6.3f", ""))
+
+
+def format_dual_pathology_gap_table(result: dict) -> str:
+    """The residual-fusion summary table of evaluate_dual_pathology's result (training_duett/evaluator.py:350-395): one row per
+    pathology (image / time-series / fusion AUROC, fusion gain, the three APs, BCE delta, correction usage, beta) and a
+    closing macro-mAP row; NaNs print as '--'."""
+    def row(label, cells):
+        out = f"{label:<12s} "
+        for (_, _, spec, sep), c in zip(_DUAL_COLS, cells):
+            out += c + sep
+        return out
+
+    width = lambda spec: int(spec.lstrip("+").split(".")[0])
+    header = row("label", [h.rjust(width(spec)) for h, _, spec, _ in _DUAL_COLS])
+    rule = "-" * len(header)
+    lines = [header, rule]
+    per = result["per_label"]
+    for r in per:
+        lines.append(row(r["name"].replace("label_", ""), [_cell(r[key], spec) for _, key, spec, _ in _DUAL_COLS]))
+
+    def macro(key):
+        vals = [r[key] for r in per if not (isinstance(r[key], float) and r[key] != r[key])]
+        return sum(vals) / len(vals) if vals else float("nan")
+
+    # closing row: blanks under the four AUROC columns, the macro means under the three AP columns (the row ends there)
+    tail = f"{'mAP (macro)':<12s} "
+    for i, (_, key, spec, sep) in enumerate(_DUAL_COLS[:7]):
+        tail += (_cell(macro(key), spec) if key.endswith("_auprc") else " " * width(spec)) + (sep if i < 6 else "")
+    lines += [rule, tail]
+    return "\n".join(lines)
+
+
+def evaluate_pathology(model, loader, device, pathology_labels) -> dict:
+    """Evaluator of the legacy `pathology_mode` teacher (stage2 / stage4 logits, training_duett/evaluator.py:100-160).  That
+    TeacherModel branch is dead in the reference snapshot and not built here (TeacherModel raises for it), so this raises too
+    instead of scoring something else."""
+    raise NotImplementedError("evaluate_pathology scores the legacy pathology_mode teacher, which is not implemented "
+                              "(only patch_dual_pathology_mode is live in the reference): use evaluate_dual_pathology")
+
+
+def format_pathology_gap_table(result: dict) -> str:
+    """Table of an evaluate_pathology result dict (training_duett/evaluator.py:163-178); kept for import compatibility."""
+    cols = (("s2_auroc", "stage2_auroc", "10.4f"), ("s4_auroc", "stage4_auroc", "10.4f"), ("gap_ro", "gap_auroc", "+8.4f"),
+            ("s2_auprc", "stage2_auprc", "10.4f"), ("s4_auprc", "stage4_auprc", "10.4f"), ("gap_pr", "gap_auprc", "+8.4f"))
+    width = lambda spec: int(spec.lstrip("+").split(".")[0])
+    lines = [f"{'label':<22s} {'n':>6s} {'pos':>7s} " + " ".join(h.rjust(width(s)) for h, _, s in cols)]
+    for r in result["per_label"]:
+        lines.append(f"{r['name']:<22s} {r['n_valid']:>6d} {r['pos_frac']:>7.4f} " + " ".join(format(r[k], s) for _, k, s in cols))
+    return "\n".join(lines)

@@ -324,3 +324,233 @@ def test_constructor_dimension_options(emu, ref, dims):
     assert rel(lp, lr_) < TOL
     lr_.backward(); lp.backward()
     _grads_match(r, p)
+
+
+@pytest.fixture(scope="module")
+def ref_engine(ref):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_engine_variants", os.path.join(REF, "training_duett", "engine.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class _StubCXR(torch.nn.Module):      # CXR embeddings ride in the pixel_values slot
+    d_out = 16
+
+    def forward(self, pv):
+        return pv[:, 0], pv[:, 1:]
+
+
+def _teacher_pair(ref, seed=18, dropout=0.0):
+    from multimodal_edema_prediction_b200.models import main_architecture_duett as A
+    torch.manual_seed(seed)
+    out = []
+    for arch in (ref[1], A):
+        duett = arch.DuettFeatureExtractor(pretrain=False, **KW)
+        perc = arch.PatchDualPathologyPerceiver(7, duett.d_representation, d_latent=32, n_heads=4, dropout=dropout,
+                                                head_hidden=16, head_dropout=dropout)
+        out.append(arch.TeacherModel(duett, _StubCXR(), perc, patch_dual_pathology_mode=True, d_img=16))
+    with torch.no_grad():
+        out[0].perceiver.correction_head[-1].weight.normal_(0, 0.05)
+        out[0].perceiver.beta.uniform_(0.5, 1.5)
+    out[1].load_state_dict(out[0].state_dict(), strict=True)
+    return out
+
+
+def _engine_batch(seed=83):
+    b = O.synth_batch(CFG, B=6, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    return {"x_ts": tuple(b["x_ts"]), "x_static": tuple(b["x_static"]), "bin_ends": tuple(b["bin_ends"]), "y": b["y"],
+            "pixel_values": torch.randn(6, 11, 16, generator=g), "y_multi": (torch.rand(6, 7, generator=g) < 0.3).float(),
+            "y_multi_mask": (torch.rand(6, 7, generator=g) < 0.9).float()}
+
+
+def _same_result(rr, pr, skip=()):
+    assert set(rr) == set(pr), set(rr) ^ set(pr)
+    for k in rr:
+        if k in skip:
+            continue
+        a, c = rr[k], pr[k]
+        if torch.is_tensor(a):
+            assert a.shape == c.shape and (rel(c.float(), a.float()) < TOL or float(a.abs().max()) < 1e-9), k
+        else:
+            assert abs(c - a) <= TOL * max(abs(a), 1e-3), (k, a, c)
+
+
+def test_engine_lp_stage_and_eval_steps(emu, ref, ref_losses, ref_engine):
+    """training_duett/engine.py: the linear-probe stage (everything eval() except the correction head; beta / correction L2
+    regularisers, aux residual KL), eval_teacher_batch, train_student_batch (frozen teacher), eval_student_batch — the
+    reference's engine on the reference's modules against the product's engine on the product's modules, same weights."""
+    from multimodal_edema_prediction_b200.loss import losses_duett as L
+    from multimodal_edema_prediction_b200.models import main_architecture_duett as A
+    from multimodal_edema_prediction_b200.training_duett import engine
+    rt, pt = _teacher_pair(ref)
+    lw, pw = torch.tensor([1.0, 0.2, 0.2, 0.2, 0.2, 0.2, 0.2]), torch.tensor([2.0, 1.5, 1.0, 3.0, 1.0, 2.5, 1.2])
+    batch, cpu = _engine_batch(), torch.device("cpu")
+    kw = dict(beta_l2=0.05, corr_l2=0.1, aux_residual_alpha=0.3)
+    rr = ref_engine.train_teacher_dual_pathology_lp_batch(batch, rt, ref_losses.DualPathologyLoss(lw, pw), torch.optim.SGD(rt.parameters(), lr=0.0), cpu, **kw)
+    pr = engine.train_teacher_dual_pathology_lp_batch(batch, pt, L.DualPathologyLoss(lw, pw), torch.optim.SGD(pt.parameters(), lr=0.0), cpu, **kw)
+    _same_result(rr, pr)
+    assert not pt.duett.training and pt.perceiver.correction_head.training and not pt.perceiver.img_cross.training
+    _grads_match_named(rt, pt)
+    bce = torch.nn.BCEWithLogitsLoss()
+    _same_result(ref_engine.eval_teacher_batch(batch, rt, bce, cpu), engine.eval_teacher_batch(batch, pt, bce, cpu))
+    # student distilled from the frozen teacher
+    torch.manual_seed(19)
+    rs = ref[1].StudentModel(ref[1].DuettFeatureExtractor(pretrain=False, **KW), pool="mean", head_hidden=16, head_dropout=0.0)
+    ps = A.StudentModel(A.DuettFeatureExtractor(pretrain=False, **KW), pool="mean", head_hidden=16, head_dropout=0.0)
+    ps.load_state_dict(rs.state_dict(), strict=True)
+    sb = _engine_batch(seed=84)
+    rr = ref_engine.train_student_batch(sb, sb, rs, rt, ref_losses.StudentKDLoss(kd_T=3.0, kd_alpha=0.4, pos_weight=2.0),
+                                        torch.optim.SGD(rs.parameters(), lr=0.0), cpu)
+    pr = engine.train_student_batch(sb, sb, ps, pt, L.StudentKDLoss(kd_T=3.0, kd_alpha=0.4, pos_weight=2.0),
+                                    torch.optim.SGD(ps.parameters(), lr=0.0), cpu)
+    _same_result(rr, pr)
+    _grads_match_named(rs, ps)
+    _same_result(ref_engine.eval_student_batch(sb, rs, cpu), engine.eval_student_batch(sb, ps, cpu))
+
+
+def _grads_match_named(r, p):
+    """_grads_match for composite modules (a Model inside a Teacher / Student: keys mapped per sub-module prefix)."""
+    from multimodal_edema_prediction_b200 import state_keys
+    from multimodal_edema_prediction_b200.duett.duett import Model
+    got = {n: (q.grad if q.grad is not None else torch.zeros_like(q)).detach() for n, q in p.named_parameters()}
+    for name, m in p.named_modules():
+        if isinstance(m, Model):
+            state_keys.to_reference(got, name + "." if name else "")
+    gs = [float(q.grad.abs().max()) for q in r.parameters() if q.grad is not None]
+    gscale = max(gs) if gs else 0.0
+    for n, q in r.named_parameters():
+        w = q.grad if q.grad is not None else torch.zeros_like(q)
+        assert (got[n].double() - w.double()).norm() <= 3e-4 * w.double().norm() + 3e-5 * gscale * max(w.numel(), 64) ** 0.5, n
+
+
+def test_checkpoint_factories_and_freezing(emu, ref, tmp_path):
+    """duett.pretrain_model / fine_tune_model (duett/duett.py:41-46), load_duett_backbone(freeze=True)
+    (models/main_architecture_duett.py:98-123), Model.freeze via freeze_encoder (duett/duett.py:485-495): a checkpoint written
+    by the REFERENCE's module is read by the product's factories; which parameters stay trainable matches the reference."""
+    from multimodal_edema_prediction_b200.duett import duett as D
+    from multimodal_edema_prediction_b200.models.main_architecture_duett import load_duett_backbone
+    torch.manual_seed(20)
+    r = ref[0].pretrain_model(**KW)
+    ck = str(tmp_path / "ssl.ckpt")
+    torch.save({"state_dict": r.state_dict()}, ck)
+    kw = {k: v for k, v in KW.items()}
+    ft_r, ft_p = ref[0].fine_tune_model(ck, freeze_encoder=True, **kw), D.fine_tune_model(ck, freeze_encoder=True, **kw)
+    assert (ft_p.pretrain, ft_p.aug_mask, ft_p.aug_noise, ft_p.lr, ft_p.weight_decay, ft_p.fusion_method) == \
+        (ft_r.pretrain, ft_r.aug_mask, ft_r.aug_noise, ft_r.lr, ft_r.weight_decay, ft_r.fusion_method)
+    assert ft_p.transformer_dropout == 0.5 and ft_p.event_transformers[0].dropout == 0.5       # duett/duett.py:44-46
+    tr_r = {n for n, q in ft_r.named_parameters() if q.requires_grad}
+    tr_p = {n for n, q in ft_p.named_parameters() if q.requires_grad}
+    assert tr_r == tr_p and tr_r and all("head" in n for n in tr_r)
+    sr, sp = ft_r.state_dict(), ft_p.state_dict()
+    assert set(sr) == set(sp) and all(torch.equal(sr[k], sp[k]) for k in sr if not k.startswith("head"))
+    # the reference's loader takes no model hyper-parameters (Lightning restores them from the checkpoint; the shim and the
+    # product fall back to the constructor defaults d_embedding=24, 2 layers, d_feedforward=512): a default-shaped checkpoint
+    torch.manual_seed(21)
+    r24 = ref[0].Model(3, 5, 1, pretrain=True, masked_transform_timesteps=4, max_len=4)
+    ck = str(tmp_path / "ssl24.ckpt")
+    torch.save({"state_dict": r24.state_dict()}, ck)
+    bb_r = ref[1].load_duett_backbone(ck, 3, 5, 4, freeze=True)
+    bb_p = load_duett_backbone(ck, 3, 5, 4, freeze=True)
+    assert not bb_p.training and not any(q.requires_grad for q in bb_p.parameters()) and not any(q.requires_grad for q in bb_r.parameters())
+    x, _ = _batch(seed=85)
+    with torch.no_grad():
+        assert rel(bb_p.encode(bb_p.feats_to_input(x, 6)), bb_r.encode(bb_r.feats_to_input(x, 6))) < TOL
+
+
+def test_evaluator_console_tables_match_the_reference(ref):
+    """format_dual_pathology_gap_table / format_pathology_gap_table (training_duett/evaluator.py:163-178,338-395; imported by
+    trainer.py:24-25): the same text as the reference's formatters on a result dict with NaNs; evaluate_pathology (legacy
+    pathology_mode teacher) raises instead of scoring something else."""
+    import importlib.util
+    import random
+    spec = importlib.util.spec_from_file_location("reference_evaluator", os.path.join(REF, "training_duett", "evaluator.py"))
+    R = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(R)
+    from multimodal_edema_prediction_b200.training_duett import evaluator as P
+    rnd = random.Random(1)
+    keys = ["img_auroc", "ts_auroc", "fus_auroc", "gap_i2f", "gap_t2f", "img_auprc", "ts_auprc", "fus_auprc", "gap_i2f_pr",
+            "gap_t2f_pr", "img_bce", "ts_bce", "fus_bce", "delta_bce", "mean_abs_corr", "corr_residual", "beta"]
+    per = []
+    for i, name in enumerate(["label_edema", "label_cardiomegaly", "x", "label_pleural_effusion_long_name"]):
+        r = {"name": name, "n_valid": 10 + i, "pos_frac": 0.1 * i}
+        r.update({k: rnd.uniform(-1, 1) for k in keys})
+        per.append(r)
+    per[2]["img_auroc"] = per[2]["gap_i2f"] = per[1]["beta"] = per[3]["img_auprc"] = float("nan")
+    res = {"labels": [r["name"] for r in per], "n": 40, "main_auroc": 0.5, "main_auprc": 0.4, "per_label": per}
+    assert P.format_dual_pathology_gap_table(res) == R.format_dual_pathology_gap_table(res)
+    for r in per:
+        r["img_auprc"] = r["ts_auprc"] = r["fus_auprc"] = float("nan")          # all-NaN macro row
+    assert P.format_dual_pathology_gap_table(res) == R.format_dual_pathology_gap_table(res)
+    per2 = [{"name": "label_a", "n_valid": 5, "pos_frac": 0.25, "stage2_auroc": 0.7, "stage4_auroc": 0.8, "gap_auroc": 0.1,
+             "stage2_auprc": 0.3, "stage4_auprc": 0.25, "gap_auprc": -0.05}]
+    assert P.format_pathology_gap_table({"per_label": per2}) == R.format_pathology_gap_table({"per_label": per2})
+    with pytest.raises(NotImplementedError):
+        P.evaluate_pathology(None, [], torch.device("cpu"), ("a",))
+    assert {n for n in dir(R) if not n.startswith("_") and callable(getattr(R, n)) and getattr(R, n).__module__ == R.__name__} \
+        <= set(dir(P)), "every public function of the reference's evaluator module exists in the product's"
+
+
+class _StubBinaryTeacher(torch.nn.Module):
+    """Any module with the teacher call signature: returns (main, aux) logits (use_aux_cxr teachers) or the main logit."""
+
+    def __init__(self, tuple_out):
+        super().__init__()
+        self.tuple_out = tuple_out
+        self.a, self.b = torch.nn.Linear(3, 1), torch.nn.Linear(16, 1)
+
+    def forward(self, x_ts, x_static, bin_ends, pixel_values):
+        main = self.a(torch.stack(list(x_static))).squeeze(-1) + torch.stack(list(x_ts)).mean((1, 2))
+        aux = self.b(pixel_values[:, 0]).squeeze(-1)
+        return (main + aux.detach(), aux) if self.tuple_out else main + aux
+
+
+class _StubPathologyTeacher(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.s2, self.s4 = torch.nn.Linear(16, 7), torch.nn.Linear(16 + 3, 7)
+
+    def forward(self, x_ts, x_static, bin_ends, pixel_values):
+        s2 = self.s2(pixel_values[:, 0])
+        s4 = self.s4(torch.cat([pixel_values[:, 1:].mean(1), torch.stack(list(x_static))], 1))
+        return {"main_logit": s4[:, 0], "stage2_logits": s2, "stage4_logits": s4}
+
+
+def test_engine_legacy_teacher_steps(emu, ref_losses, ref_engine):
+    """train_teacher_batch (tensor or (main, aux) tuple teachers, aux_alpha) and train_teacher_pathology_batch
+    (PathologyMultiLabelLoss) — training_duett/engine.py:41-74,93-130: model-agnostic steps, compared with the reference's
+    engine on stub teachers (the legacy TeacherModel modes that produce such outputs are not built)."""
+    import copy
+    from multimodal_edema_prediction_b200.loss import losses_duett as L
+    from multimodal_edema_prediction_b200.training_duett import engine
+    batch, cpu = _engine_batch(seed=86), torch.device("cpu")
+    bce = torch.nn.BCEWithLogitsLoss()
+    for tuple_out in (True, False):
+        torch.manual_seed(23)
+        t_r = _StubBinaryTeacher(tuple_out)
+        t_p = copy.deepcopy(t_r)
+        rr = ref_engine.train_teacher_batch(batch, t_r, bce, torch.optim.SGD(t_r.parameters(), lr=0.1), cpu, aux_alpha=0.3)
+        pr = engine.train_teacher_batch(batch, t_p, bce, torch.optim.SGD(t_p.parameters(), lr=0.1), cpu, aux_alpha=0.3)
+        _same_result(rr, pr)
+        for a, c in zip(t_r.parameters(), t_p.parameters()):
+            assert torch.allclose(a, c, atol=1e-7)                       # the optimizer step happened, identically
+    torch.manual_seed(24)
+    t_r = _StubPathologyTeacher()
+    t_p = copy.deepcopy(t_r)
+    lw = torch.rand(7) + 0.1
+    rr = ref_engine.train_teacher_pathology_batch(batch, t_r, ref_losses.PathologyMultiLabelLoss(lw, None, 0.5, 1.0),
+                                                  torch.optim.SGD(t_r.parameters(), lr=0.1), cpu)
+    pr = engine.train_teacher_pathology_batch(batch, t_p, L.PathologyMultiLabelLoss(lw, None, 0.5, 1.0),
+                                              torch.optim.SGD(t_p.parameters(), lr=0.1), cpu)
+    _same_result(rr, pr)
+    for a, c in zip(t_r.parameters(), t_p.parameters()):
+        assert torch.allclose(a, c, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        engine.train_teacher_pathology_batch(batch, _StubBinaryTeacher(False), L.PathologyMultiLabelLoss(lw), None, cpu)
+    # every public function of the reference's engine exists with the same parameter names
+    import inspect
+    for name, fn in vars(ref_engine).items():
+        if inspect.isfunction(fn) and not name.startswith("_") and fn.__module__ == ref_engine.__name__:
+            assert list(inspect.signature(getattr(engine, name)).parameters) == list(inspect.signature(fn).parameters), name
