@@ -501,6 +501,13 @@ def ssl_mask(xs, step, ev, keep):
     return xc, y_ts, y_mask, y_ev, y_ev_mask
 
 
+def bin_events(slot, vals, cnts, row_start, means, stds, T):
+    """Contract of dx_bin_events = the reference's build_stay_tensor row walk (oracle/binning_oracle.py, pinned by g5)."""
+    from oracle import binning_oracle
+    return torch.from_numpy(binning_oracle.bin_events(slot.numpy(), vals.numpy(), cnts.numpy(), row_start.numpy(),
+                                                      means.numpy(), stds.numpy(), int(T)))
+
+
 def cast_into(x, y):
     y.copy_(x)
     return y
@@ -538,7 +545,7 @@ EMULATED = ["binary_auc", "sum_n", "dropout", "rowdot_bias", "gemm_", "relayout_
             "attn_fwd", "attn_bwd", "attn_probs_mean", "embed_fwd", "embed_bwd", "bn2d_fwd", "bn2d_bwd", "layernorm_fwd", "layernorm_bwd",
             "mean_rows", "mean_rows_bwd", "gather_vec", "scatter_vec", "kd_loss", "bce_logits", "masked_mse_bce",
             "masked_bce_cols", "aux_residual_kl", "require_device", "act_bwd", "act_fwd", "scale_dev", "sum_div_acc", "fusion_logits",
-            "fusion_logits_bwd", "adamw", "sumsq", "clip_factor", "cast_into", "ssl_mask"]
+            "fusion_logits_bwd", "adamw", "sumsq", "clip_factor", "cast_into", "ssl_mask", "bin_events"]
 
 
 def install(monkeypatch):

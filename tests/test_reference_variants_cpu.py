@@ -554,3 +554,51 @@ def test_engine_legacy_teacher_steps(emu, ref_losses, ref_engine):
     for name, fn in vars(ref_engine).items():
         if inspect.isfunction(fn) and not name.startswith("_") and fn.__module__ == ref_engine.__name__:
             assert list(inspect.signature(getattr(engine, name)).parameters) == list(inspect.signature(fn).parameters), name
+
+
+def test_mimic_dataset_matches_the_reference_dataset(emu, ref):
+    """duett/mimic_dataset.py: MIMICDataset (host-only StayRows items binned per batch) + collate_into_seqs + encode_static +
+    the d_* / pos_frac accessors against the reference's Dataset on synthetic frames — several rows per slot, slots beyond
+    T, zero / NaN counts, NaN values and ages, a variable pair sharing one count column."""
+    import pandas as pd
+    import duett.mimic_dataset as R
+    from multimodal_edema_prediction_b200.duett import mimic_dataset as P
+    from multimodal_edema_prediction_b200.duett.duett import Model
+    rng = np.random.default_rng(3)
+    T, V, B = 6, 4, 5
+    all_vars = [f"v{j}" for j in range(V)]
+    all_counts = ["c0", "c1", "c1", "c3"]                       # v1 and v2 share a count column
+    rows = []
+    for b in range(B):
+        for _ in range(int(rng.integers(1, 9))):
+            r = {"stay_id": 100 + b, "slot_idx": int(rng.integers(0, T + 2))}
+            r.update({v: float(rng.normal()) for v in all_vars})
+            r.update({c: float(rng.integers(0, 4)) for c in set(all_counts)})
+            rows.append(r)
+    icu = pd.DataFrame(rows)
+    icu.loc[1, "v0"], icu.loc[2, "c1"] = np.nan, np.nan
+    static = pd.DataFrame({"stay_id": [100 + b for b in range(B)], "age_at_intime": [30.0, np.nan, 55.0, 71.5, 90.0],
+                           "s0": [1, 0, 1, 0, 1], "s1": [0, 1, 0, 1, 0], "label": [0.0, 1.0, 1.0, 0.0, 1.0]})
+    meta = {"N_TIMESTEPS": T, "LABEL_COL": "label", "age_mean": 60.0, "age_std": 12.0, "ONEHOT_STATIC": ["s0", "s1"],
+            "means": {v: float(rng.normal()) for v in all_vars}, "stds": {v: float(abs(rng.normal()) + 0.2) for v in all_vars},
+            "ALL_VARS": all_vars, "ALL_COUNTS": all_counts, "D_STATIC": 3}
+    ids = [100 + b for b in range(B)]
+    rd, pd_ = R.MIMICDataset(ids, icu, static, meta), P.MIMICDataset(ids, icu, static, meta, device="cpu")   # (default: the CUDA device)
+    assert len(rd) == len(pd_) == B and rd.pos_frac() == pd_.pos_frac()
+    assert (rd.d_static_num(), rd.d_time_series_num(), rd.d_target()) == (pd_.d_static_num(), pd_.d_time_series_num(), pd_.d_target())
+    r_batch = R.collate_into_seqs([rd[i] for i in range(B)])
+    p_batch = P.collate_into_seqs([pd_[i] for i in range(B)])
+    assert r_batch[1] == p_batch[1]                                                   # labels
+    assert all(isinstance(s, P.StayRows) and s.shape == (T, 2 * V) for s in p_batch[0][0])
+    for a, c in zip(r_batch[0][1], p_batch[0][1]):
+        assert torch.equal(a, c)                                                      # encode_static (NaN age -> 0)
+    for a, c in zip(r_batch[0][2], p_batch[0][2]):
+        assert torch.equal(a, c)                                                      # bin_ends
+    model = Model(3, V, 1, d_embedding=8, masked_transform_timesteps=T, max_len=T, n_duett_layers=1, pretrain=False).eval()
+    xs_static, xs_ts, xs_times, n_ts = model.feats_to_input(p_batch[0], B)
+    want = torch.stack(list(r_batch[0][0]))
+    assert np.array_equal(xs_ts[:, :, :-1].numpy(), want.numpy(), equal_nan=True) and float(xs_ts[:, :, -1].abs().sum()) == 0
+    assert n_ts == [T] * B and torch.equal(xs_static, torch.stack(list(r_batch[0][1])))
+    (bx_ts, bx_static, bx_times), by = pd_.batch([3, 0, 4])                            # the one-launch batch builder
+    assert by == tuple(r_batch[1][i] for i in (3, 0, 4))
+    assert np.array_equal(torch.stack(bx_ts).numpy(), want[[3, 0, 4]].numpy(), equal_nan=True)
