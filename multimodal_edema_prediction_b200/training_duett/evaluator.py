@@ -32,6 +32,14 @@ def _gather_all(t: torch.Tensor) -> torch.Tensor:
     return torch.cat([p[:s] for p, s in zip(parts, sizes)])
 
 
+def _ap_like_sklearn(auprc: float, n_pos: float) -> float:
+    """dx_binary_auc reports the average precision of a label set without positives as NaN (undefined).  The reference scores
+    with sklearn's average_precision_score, which since scikit-learn 1.1 warns and returns 0.0 there ("no positive class
+    found in y_true, recall is set to one for all thresholds") — and that 0.0 enters the reference's macro means
+    (training_duett/evaluator.py:322-331).  Follow the installed-sklearn behaviour of the reference."""
+    return 0.0 if n_pos == 0 else auprc
+
+
 def binary_metrics(logits: torch.Tensor, y: torch.Tensor) -> dict:
     """{"auroc","auprc","n","pos_frac"} of sigmoid(logits) against y, computed on the device (one D2H read of 4 doubles)."""
     logits = _gather_all(logits.detach().reshape(-1).float())
@@ -39,7 +47,7 @@ def binary_metrics(logits: torch.Tensor, y: torch.Tensor) -> dict:
     if logits.numel() == 0:
         return {"auroc": float("nan"), "auprc": float("nan"), "n": 0, "pos_frac": float("nan")}
     auroc, auprc, n_pos, n = ops.binary_auc(logits, y, apply_sigmoid=True).tolist()
-    return {"auroc": float(auroc), "auprc": float(auprc), "n": int(n), "pos_frac": float(n_pos / n)}
+    return {"auroc": float(auroc), "auprc": float(_ap_like_sklearn(auprc, n_pos)), "n": int(n), "pos_frac": float(n_pos / n)}
 
 
 @torch.no_grad()
@@ -161,7 +169,7 @@ def evaluate_dual_pathology(model, loader, device, pathology_labels, *, query_re
         if yk.numel() == 0:
             return nan, nan
         r = ops.binary_auc(logits, yk, apply_sigmoid=True).tolist()
-        return float(r[0]), float(r[1])
+        return float(r[0]), float(_ap_like_sklearn(r[1], r[2]))
 
     per_label = []
     for k in range(K):

@@ -602,3 +602,72 @@ def test_mimic_dataset_matches_the_reference_dataset(emu, ref):
     (bx_ts, bx_static, bx_times), by = pd_.batch([3, 0, 4])                            # the one-launch batch builder
     assert by == tuple(r_batch[1][i] for i in (3, 0, 4))
     assert np.array_equal(torch.stack(bx_ts).numpy(), want[[3, 0, 4]].numpy(), equal_nan=True)
+
+
+def test_evaluators_match_the_reference_evaluators(emu, ref):
+    """evaluate_dual_pathology / evaluate_binary against the reference's own functions (training_duett/evaluator.py:10-37,
+    197-335; sklearn on the host there, the ranking kernel's contract here) on a stub teacher: a label with a single class
+    (AUROC undefined), a label with one valid sample (Pearson undefined), tied logits.  (A label that is NEVER valid makes the
+    reference's sklearn call raise IndexError past its `except ValueError`; the product reports NaNs for it.)"""
+    import training_duett.evaluator as R
+    from multimodal_edema_prediction_b200.training_duett import evaluator as P
+    K, labels = 5, ("label_a", "label_b", "label_c", "label_d", "label_e")
+    g = torch.Generator().manual_seed(9)
+
+    class Perc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.beta = torch.nn.Parameter(torch.tensor([0.5, 1.0, 1.5, 2.0, 0.1]))
+
+    class Teacher(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.perceiver = Perc()
+
+        def forward(self, x_ts, x_static, bin_ends, pv):
+            img = (pv[:, :K] * 4).round() / 4                         # quantised: ties between samples
+            corr = 0.3 * pv[:, K:2 * K]
+            return {"img_logits": img, "ts_logits": pv[:, 2 * K:3 * K], "fusion_logits": img + corr, "scaled_correction": corr,
+                    "main_logit": img[:, 0] + corr[:, 0]}
+
+    batches = []
+    for i in range(4):
+        n = 11
+        ym = (torch.rand(n, K, generator=g) < 0.4).float()
+        mk = (torch.rand(n, K, generator=g) < 0.8).float()
+        ym[:, 2] = 1.0                                                # one class only
+        mk[:, 3] = 0.0
+        if i == 2:
+            mk[4, 3] = 1.0                                            # exactly one valid sample
+        batches.append({"x_ts": tuple(torch.randn(2, 3, generator=g) for _ in range(n)),
+                        "x_static": tuple(torch.zeros(1) for _ in range(n)), "bin_ends": tuple(torch.zeros(1) for _ in range(n)),
+                        "y": (torch.rand(n, generator=g) < 0.5).float(), "pixel_values": torch.randn(n, 3 * K, generator=g),
+                        "y_multi": ym, "y_multi_mask": mk})
+    model, cpu = Teacher(), torch.device("cpu")
+    rr, pr = R.evaluate_dual_pathology(model, batches, cpu, labels), P.evaluate_dual_pathology(model, batches, cpu, labels)
+
+    def close(a, c, what):
+        if isinstance(a, float) and a != a:
+            assert c != c, (what, a, c)
+        elif isinstance(a, (int, float)):
+            assert abs(a - c) <= 2e-6 * max(1.0, abs(a)), (what, a, c)
+        else:
+            assert a == c, (what, a, c)
+
+    assert set(rr) == set(pr)
+    for k in ("labels", "n", "main_auroc", "main_auprc"):
+        close(rr[k], pr[k], k)
+    for a, c in zip(rr["per_label"], pr["per_label"]):
+        assert set(a) == set(c)
+        for k in a:
+            close(a[k], c[k], (a["name"], k))
+    assert P.format_dual_pathology_gap_table(pr).count("--") == R.format_dual_pathology_gap_table(rr).count("--") > 0
+    for b in batches:
+        b["y_multi_mask"][:, 1] = 0.0                                 # never valid: NaNs, n_valid 0 (the reference raises here)
+    never = P.evaluate_dual_pathology(model, batches, cpu, labels)["per_label"][1]
+    assert never["n_valid"] == 0 and all(never[k] != never[k] for k in ("img_auroc", "fus_auprc", "img_bce", "pos_frac", "corr_residual"))
+    fwd_r, fwd_p = R.make_teacher_forward(), P.make_teacher_forward()
+    rb, pb = R.evaluate_binary(model, batches, cpu, fwd_r), P.evaluate_binary(model, batches, cpu, fwd_p)
+    assert set(rb) == set(pb)
+    for k in rb:
+        close(rb[k], pb[k], k)
