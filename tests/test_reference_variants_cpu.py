@@ -115,7 +115,10 @@ def test_supervised_fusion_methods_train_and_eval(emu, ref, fusion):
 
 
 @pytest.mark.parametrize("opts", [dict(pretrain_n_hidden=1, pretrain_d_hidden=16), dict(predict_events=False),
-                                  dict(pretrain_dropout=0.0), dict(pretrain_presence_weight=0.7)])
+                                  dict(pretrain_dropout=0.0), dict(pretrain_presence_weight=0.7),
+                                  dict(pretrain_masked_steps=3), dict(pretrain_masked_steps=4, pretrain_dropout=0.0),
+                                  dict(pretrain_masked_steps=2, pretrain_n_hidden=1, pretrain_d_hidden=16),
+                                  dict(pretrain_masked_steps=2, predict_events=False, pretrain_presence=False)])
 def test_ssl_step_option_variants(emu, ref, opts):
     """Model.training_step(pretrain=True) with SSL heads that have a hidden layer + BatchNorm (pretrain_n_hidden=1), without
     event prediction, without variable dropout, with another presence weight: masking bit-exact, loss and gradients."""
