@@ -674,3 +674,64 @@ def test_evaluators_match_the_reference_evaluators(emu, ref):
     assert set(rb) == set(pb)
     for k in rb:
         close(rb[k], pb[k], k)
+
+
+def test_engine_steps_with_frozen_parts(emu, ref, ref_losses, ref_engine):
+    """The trainer's freezing patterns (training_duett/trainer.py:170-207, engine.py:7-20): (1) a fully frozen DuETT backbone
+    goes to eval() inside the teacher step (running BatchNorm statistics) while the fusion head trains; (2) the LP stage
+    with everything frozen except perceiver.correction_head and beta, and the correction head's Dropout probability
+    overridden through its nn.Dropout modules (p = 0 here so both sides are deterministic)."""
+    from multimodal_edema_prediction_b200.loss import losses_duett as L
+    from multimodal_edema_prediction_b200.training_duett import engine
+    lw, pw = torch.tensor([1.0, 0.2, 0.2, 0.2, 0.2, 0.2, 0.2]), torch.tensor([2.0, 1.5, 1.0, 3.0, 1.0, 2.5, 1.2])
+    batch, cpu = _engine_batch(seed=87), torch.device("cpu")
+    # (1) frozen backbone
+    rt, pt = _teacher_pair(ref, seed=25)
+    for t in (rt, pt):
+        for q in t.duett.parameters():
+            q.requires_grad = False
+    rr = ref_engine.train_teacher_dual_pathology_batch(batch, rt, ref_losses.DualPathologyLoss(lw, pw),
+                                                       torch.optim.SGD([q for q in rt.parameters() if q.requires_grad], lr=0.0),
+                                                       cpu, aux_residual_alpha=0.2)
+    pr = engine.train_teacher_dual_pathology_batch(batch, pt, L.DualPathologyLoss(lw, pw),
+                                                   torch.optim.SGD([q for q in pt.parameters() if q.requires_grad], lr=0.0),
+                                                   cpu, aux_residual_alpha=0.2)
+    _same_result(rr, pr)
+    assert not pt.duett.training and pt.perceiver.training and not rt.duett.training
+    assert all(q.grad is None for q in pt.duett.parameters())
+    for (n, a), (_, c) in zip(rt.perceiver.named_parameters(), pt.perceiver.named_parameters()):
+        w = a.grad if a.grad is not None else torch.zeros_like(a)
+        g = c.grad if c.grad is not None else torch.zeros_like(c)
+        assert (g - w).norm() <= 3e-4 * w.norm() + 1e-6, n
+    sr, sp = rt.state_dict(), pt.state_dict()
+    assert all(torch.equal(sr[k], sp[k]) for k in sr if "running" in k or "num_batches" in k)      # frozen BN did not move
+    # (2) LP stage: only the correction head + beta train
+    rt, pt = _teacher_pair(ref, seed=26, dropout=0.1)
+    for t in (rt, pt):
+        for q in t.parameters():
+            q.requires_grad = False
+        for q in t.perceiver.correction_head.parameters():
+            q.requires_grad = True
+        t.perceiver.beta.requires_grad = True
+        n_drop = 0
+        for m in t.perceiver.correction_head.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+                n_drop += 1
+        assert n_drop == 1
+    kw = dict(beta_l2=0.02, corr_l2=0.3, aux_residual_alpha=0.1)
+    rr = ref_engine.train_teacher_dual_pathology_lp_batch(batch, rt, ref_losses.DualPathologyLoss(lw, pw),
+                                                          torch.optim.SGD([q for q in rt.parameters() if q.requires_grad], lr=0.0), cpu, **kw)
+    pr = engine.train_teacher_dual_pathology_lp_batch(batch, pt, L.DualPathologyLoss(lw, pw),
+                                                      torch.optim.SGD([q for q in pt.parameters() if q.requires_grad], lr=0.0), cpu, **kw)
+    _same_result(rr, pr)
+    assert all(q.grad is None for q in pt.duett.parameters()) and all(q.grad is None for q in rt.duett.parameters())
+    pn = dict(pt.named_parameters())
+    for n, a in rt.named_parameters():
+        if n.startswith("duett."):
+            continue
+        c = pn[n]                                                    # perceiver / img_proj names are the reference's
+        assert (a.grad is None) == (c.grad is None), n
+        if a.grad is not None:
+            assert n.startswith("perceiver.correction_head") or n == "perceiver.beta", n
+            assert (c.grad - a.grad).norm() <= 3e-4 * a.grad.norm() + 1e-7, n
