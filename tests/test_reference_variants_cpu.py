@@ -735,3 +735,38 @@ def test_engine_steps_with_frozen_parts(emu, ref, ref_losses, ref_engine):
         if a.grad is not None:
             assert n.startswith("perceiver.correction_head") or n == "perceiver.beta", n
             assert (c.grad - a.grad).norm() <= 3e-4 * a.grad.norm() + 1e-7, n
+
+
+def test_multi_step_training_and_gradient_accumulation(emu, ref, ref_losses):
+    """Three AdamW steps of the KD student (BatchNorm running statistics evolve, gradients are re-created every step) and a
+    two-micro-batch gradient accumulation (no zero_grad in between): parameters and buffers stay in step with the reference's
+    modules under the same torch optimizer — the product's kernels accumulate straight into .grad, so stale or doubly counted
+    gradients would show here."""
+    from multimodal_edema_prediction_b200 import state_keys
+    from multimodal_edema_prediction_b200.loss import losses_duett as L
+    from multimodal_edema_prediction_b200.models import main_architecture_duett as A
+    torch.manual_seed(27)
+    rs = ref[1].StudentModel(ref[1].DuettFeatureExtractor(pretrain=False, **KW), pool="mean", head_hidden=16, head_dropout=0.0)
+    ps = A.StudentModel(A.DuettFeatureExtractor(pretrain=False, **KW), pool="mean", head_hidden=16, head_dropout=0.0)
+    ps.load_state_dict(rs.state_dict(), strict=True)
+    rs.train(); ps.train()
+    ro, po = torch.optim.AdamW(rs.parameters(), lr=3e-3, weight_decay=0.05), torch.optim.AdamW(ps.parameters(), lr=3e-3, weight_decay=0.05)
+    rl, pl = ref_losses.StudentKDLoss(kd_T=2.0, kd_alpha=0.5), L.StudentKDLoss(kd_T=2.0, kd_alpha=0.5)
+    g = torch.Generator().manual_seed(28)
+    for step in range(3):
+        ro.zero_grad(); po.zero_grad()
+        for micro in range(2 if step == 1 else 1):                  # step 1 accumulates two micro-batches
+            x, b = _batch(seed=90 + 10 * step + micro)
+            z_t = torch.randn(6, generator=g)
+            lr_ = rl(rs(x[0], x[1], list(x[2])), z_t, b["y"])["total"]
+            lp = pl(ps(x[0], x[1], list(x[2])), z_t, b["y"])["total"]
+            assert rel(lp, lr_) < 2e-4, (step, micro)
+            lr_.backward(); lp.backward()
+        ro.step(); po.step()
+    sr, sp = rs.state_dict(), ps.state_dict()
+    assert set(sr) == set(sp)
+    for k in sr:
+        if sr[k].dtype.is_floating_point:
+            assert (sp[k] - sr[k]).norm() <= 2e-3 * sr[k].norm() + 1e-5, k      # AdamW normalises: early steps amplify fp32 noise
+        else:
+            assert torch.equal(sp[k], sr[k]), k
