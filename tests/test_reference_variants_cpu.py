@@ -770,3 +770,55 @@ def test_multi_step_training_and_gradient_accumulation(emu, ref, ref_losses):
             assert (sp[k] - sr[k]).norm() <= 2e-3 * sr[k].norm() + 1e-5, k      # AdamW normalises: early steps amplify fp32 noise
         else:
             assert torch.equal(sp[k], sr[k]), k
+
+
+def test_real_mimic_working_point(emu, ref, ref_losses, ref_engine):
+    """The reference's real configuration (d_embedding 24, 2+2 layers, T = 24 hourly bins, V = 34 variables, 24
+    static features, heads 2, d_ff 512 -> E = 600, E' = 840 whose x_transformers FFN width is int(dim * (512 / dim))): one
+    teacher step through the engines and one SSL step, product next to the reference."""
+    from multimodal_edema_prediction_b200.duett.duett import Model
+    from multimodal_edema_prediction_b200.loss import losses_duett as L
+    from multimodal_edema_prediction_b200.models import main_architecture_duett as A
+    from multimodal_edema_prediction_b200.training_duett import engine
+    cfg = O.DuettConfig(d_static_num=24, d_time_series_num=34, n_timesteps=24, d_embedding=24, n_layers=2)
+    kw = dict(d_static_num=24, d_time_series_num=34, d_target=1, masked_transform_timesteps=24, max_len=24)
+    B = 4
+    b = O.synth_batch(cfg, B=B, seed=91)
+    g = torch.Generator().manual_seed(92)
+    batch = {"x_ts": tuple(b["x_ts"]), "x_static": tuple(b["x_static"]), "bin_ends": tuple(b["bin_ends"]), "y": b["y"],
+             "pixel_values": torch.randn(B, 1 + 49, 768, generator=g), "y_multi": (torch.rand(B, 7, generator=g) < 0.3).float(),
+             "y_multi_mask": (torch.rand(B, 7, generator=g) < 0.9).float()}
+
+    class CXR(torch.nn.Module):
+        d_out = 768
+
+        def forward(self, pv):
+            return pv[:, 0], pv[:, 1:]
+
+    torch.manual_seed(29)
+    teachers = []
+    for arch in (ref[1], A):
+        duett = arch.DuettFeatureExtractor(pretrain=False, **kw)
+        perc = arch.PatchDualPathologyPerceiver(7, duett.d_representation, d_latent=256, n_heads=4, dropout=0.0, head_hidden=64,
+                                                head_dropout=0.0)
+        teachers.append(arch.TeacherModel(duett, CXR(), perc, patch_dual_pathology_mode=True, d_img=768))
+    rt, pt = teachers
+    assert pt.duett.event_transformers[0].ff_inner == int(600 * (512 / 600)) and pt.duett.time_transformers[0].ff_inner == int(840 * (512 / 840))
+    with torch.no_grad():
+        rt.perceiver.correction_head[-1].weight.normal_(0, 0.05)
+    pt.load_state_dict(rt.state_dict(), strict=True)
+    lw, cpu = torch.tensor([1.0, 0.2, 0.2, 0.2, 0.2, 0.2, 0.2]), torch.device("cpu")
+    rr = ref_engine.train_teacher_dual_pathology_batch(batch, rt, ref_losses.DualPathologyLoss(lw), torch.optim.SGD(rt.parameters(), lr=0.0), cpu,
+                                                       aux_residual_alpha=0.3)
+    pr = engine.train_teacher_dual_pathology_batch(batch, pt, L.DualPathologyLoss(lw), torch.optim.SGD(pt.parameters(), lr=0.0), cpu,
+                                                   aux_residual_alpha=0.3)
+    _same_result(rr, pr)
+    _grads_match_named(rt, pt)
+    r, p = _pair(ref[0].Model, Model, seed=30, pretrain=True, **kw)
+    r.train(); p.train()
+    x = (tuple(b["x_ts"]), tuple(b["x_static"]), list(b["bin_ends"]))
+    r.rng, p.rng = np.random.default_rng(8), np.random.default_rng(8)
+    lr_, lp = r.training_step((x, tuple([0.0] * B)), 0), p.training_step((x, tuple([0.0] * B)), 0)
+    assert rel(lp, lr_) < TOL
+    lr_.backward(); lp.backward()
+    _grads_match(r, p)
